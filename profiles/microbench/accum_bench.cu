@@ -1,0 +1,100 @@
+// Micro-benchmark: cost of the sparse-accumulate primitive on sm_100a.
+// Streams (col,val) products from HBM and accumulates into a per-CTA table.
+// Variants: 0 stream only, 1 smem float atomicAdd (CAS loop), 2 racy LDS/FADD/STS (upper bound, wrong),
+// 3 smem native int atomicAdd, 4 global RED.ADD.F32 into an L2-resident table,
+// 5 warp-private table, 8-lane sub-steps (conflict free, no atomics), 6 warp-private full-warp racy-free (one B row per warp instr).
+#include <cstdio>
+#include <cstdlib>
+#include <cstdint>
+#include <vector>
+#include <cuda_runtime.h>
+#define CK(x) do{cudaError_t e=(x); if(e!=cudaSuccess){printf("CUDA error %s at %d\n",cudaGetErrorString(e),__LINE__); exit(1);} }while(0)
+
+template<int MODE>
+__global__ void __launch_bounds__(1024) bench(const int* __restrict__ cols, const float* __restrict__ vals,
+                      long n_per_cta, int W, float* __restrict__ gacc, float* __restrict__ out)
+{
+    extern __shared__ float acc[];
+    int* iacc = (int*)acc;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    if (MODE != 4) { for (int i = tid; i < W; i += nt) acc[i] = 0.f; }
+    __syncthreads();
+    const int* c = cols + (long)blockIdx.x * n_per_cta;
+    const float* v = vals + (long)blockIdx.x * n_per_cta;
+    float* g = gacc + (long)blockIdx.x * W;
+    float s = 0.f;
+    const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+    const int Ww = W / nw;  // warp-private width
+    float* wacc = acc + warp * Ww;
+    for (long i = tid; i < n_per_cta; i += 4L * nt) {
+        int ci[4]; float vi[4];
+        #pragma unroll
+        for (int j = 0; j < 4; j++) { long p = i + (long)j * nt; bool ok = p < n_per_cta; ci[j] = ok ? __ldg(c + p) : 0; vi[j] = ok ? __ldg(v + p) : 0.f; }
+        #pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (MODE == 0) { s += vi[j] * (float)ci[j]; }
+            else if (MODE == 1) { atomicAdd(&acc[ci[j]], vi[j]); }
+            else if (MODE == 2) { acc[ci[j]] += vi[j]; }
+            else if (MODE == 3) { atomicAdd(&iacc[ci[j]], __float_as_int(vi[j]) & 0xff); }
+            else if (MODE == 4) { atomicAdd(&g[ci[j]], vi[j]); }
+            else if (MODE == 5) {
+                int cc = ci[j] % Ww;
+                #pragma unroll
+                for (int q = 0; q < 4; q++) { if ((lane >> 3) == q) { wacc[cc] += vi[j]; } __syncwarp(); }
+            }
+            else if (MODE == 6) { int cc = ci[j] % Ww; wacc[cc] += vi[j]; __syncwarp(); }
+        }
+    }
+    __syncthreads();
+    if (MODE == 0) { if (s == 123.456f) out[0] = s; }
+    else if (MODE != 4) { float t = 0; for (int i = tid; i < W; i += nt) t += acc[i]; if (t == 123.456f) out[0] = t; }
+}
+
+template<int MODE>
+void run(const char* name, int threads, int ctas_per_sm, int W, const int* cols, const float* vals, long N, float* gacc, float* out, int nsm) {
+    int grid = nsm * ctas_per_sm;
+    long n_per_cta = N / grid;
+    size_t smem = (MODE == 4) ? 0 : (size_t)W * 4;
+    CK(cudaFuncSetAttribute(bench<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int it = 0; it < 4; it++) {
+        CK(cudaEventRecord(e0));
+        bench<MODE><<<grid, threads, smem>>>(cols, vals, n_per_cta, W, gacc, out);
+        CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+        float ms; cudaEventElapsedTime(&ms, e0, e1); if (it > 0 && ms < best) best = ms;
+    }
+    CK(cudaGetLastError());
+    double prods = (double)n_per_cta * grid;
+    printf("%-28s thr=%4d cta/sm=%d W=%6d  %8.3f ms  %7.2f Gprod/s  %6.1f GB/s stream\n", name, threads, ctas_per_sm, W, best, prods / best / 1e6, prods * 8 / best / 1e6);
+    fflush(stdout);
+}
+
+int main() {
+    cudaDeviceProp p; CK(cudaGetDeviceProperties(&p, 0));
+    int nsm = p.multiProcessorCount; printf("device %s SMs=%d\n", p.name, nsm);
+    const long N = 1L << 28;  // 268M products = 2 GiB of (col,val)
+    int* cols; float* vals; float* gacc; float* out;
+    CK(cudaMalloc(&cols, N * 4)); CK(cudaMalloc(&vals, N * 4)); CK(cudaMalloc(&out, 64));
+    CK(cudaMalloc(&gacc, (size_t)nsm * 4 * 50000 * 4));
+    CK(cudaMemset(gacc, 0, (size_t)nsm * 4 * 50000 * 4));
+    for (int W : {49152, 24576}) {
+        std::vector<int> h(1 << 24); uint64_t s = 88172645463325252ULL;
+        for (auto& x : h) { s ^= s << 13; s ^= s >> 7; s ^= s << 17; x = (int)(s % (uint64_t)W); }
+        for (long o = 0; o < N; o += (1 << 24)) CK(cudaMemcpy(cols + o, h.data(), (size_t)(1 << 24) * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemset(vals, 0x3c, N * 4));
+        int cps = (W == 49152) ? 1 : 2;
+        int thr = (W == 49152) ? 1024 : 512;
+        printf("--- W=%d\n", W);
+        run<0>("stream only", thr, cps, W, cols, vals, N, gacc, out, nsm);
+        run<1>("smem float atomicAdd (CAS)", thr, cps, W, cols, vals, N, gacc, out, nsm);
+        run<2>("smem racy RMW (bound)", thr, cps, W, cols, vals, N, gacc, out, nsm);
+        run<3>("smem int atomicAdd native", thr, cps, W, cols, vals, N, gacc, out, nsm);
+        run<4>("global RED.ADD.F32 (L2)", thr, cps, W, cols, vals, N, gacc, out, nsm);
+        run<5>("warp-private 8-lane substeps", thr, cps, W, cols, vals, N, gacc, out, nsm);
+        run<6>("warp-private full-warp RMW", thr, cps, W, cols, vals, N, gacc, out, nsm);
+        if (W == 49152) { run<1>("smem float atomicAdd (CAS)", 512, 1, W, cols, vals, N, gacc, out, nsm); run<1>("smem float atomicAdd (CAS)", 256, 1, W, cols, vals, N, gacc, out, nsm); }
+        else { run<1>("smem float atomicAdd (CAS)", 1024, 2, W, cols, vals, N, gacc, out, nsm); run<1>("smem float atomicAdd (CAS)", 256, 2, W, cols, vals, N, gacc, out, nsm);}
+    }
+    return 0;
+}
