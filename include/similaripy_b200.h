@@ -1,0 +1,226 @@
+/*
+ * similaripy_b200.h -- C ABI of the B200-native sparse-KNN similarity hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch / scipy types.
+ * Each entry point names the reference interface it replaces (paths relative to
+ * the upstream repository bogliosimone/similaripy @ a16d939, v0.6.0).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative spy_status on failure;
+ *     spy_last_error() returns a thread-local, NUL-terminated description.
+ *   - "_dev" functions take DEVICE pointers and a cudaStream_t passed as void*;
+ *     they are asynchronous on that stream and never synchronise the device.
+ *   - "_host" functions take HOST pointers, allocate/copy/free what they need on
+ *     the current device and return when the outputs are complete.
+ *   - CSR index arrays are int32 (the reference kernel is instantiated for
+ *     <int,float> only, s_plus.pyx:360); offsets into the output slab are 64-bit.
+ *   - library is re-entrant per (device, stream); no global mutable state except
+ *     the cached SM count per device.
+ */
+#ifndef SIMILARIPY_B200_H_
+#define SIMILARIPY_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPY_ABI_VERSION 1
+
+typedef enum {
+    SPY_OK = 0,
+    SPY_ERR_CUDA = -1,       /* a CUDA runtime call failed (see spy_last_error) */
+    SPY_ERR_INVALID = -2,    /* bad argument / enum                              */
+    SPY_ERR_NOMEM = -3,      /* device allocation failed                          */
+    SPY_ERR_UNSUPPORTED = -4 /* configuration outside what the kernels cover      */
+} spy_status;
+
+/* column selection modes == s_plus::SelectionMode (s_plus.h:24-28) */
+#define SPY_SEL_NONE 0
+#define SPY_SEL_ARRAY 1
+#define SPY_SEL_MATRIX 2
+
+/* TF / IDF modes == normalization.pyx:12-24 */
+#define SPY_TF_BINARY 0
+#define SPY_TF_RAW 1
+#define SPY_TF_SQRT 2
+#define SPY_TF_FREQ 3
+#define SPY_TF_LOG 4
+#define SPY_IDF_UNARY 0
+#define SPY_IDF_BASE 1
+#define SPY_IDF_SMOOTH 2
+#define SPY_IDF_PROB 3
+#define SPY_IDF_BM25 4
+
+/* value / index dtypes of the normalizer entry points (Cython fused types
+ * floating x integral, normalization.pyx:97-102) */
+#define SPY_F32 0
+#define SPY_F64 1
+#define SPY_I32 0
+#define SPY_I64 1
+/* extra source dtypes accepted by spy_cast_values_dev (matrix.data.astype(float32), s_plus_utils.pyx:307-308) */
+#define SPY_VAL_I32 2
+#define SPY_VAL_I64 3
+
+/* ---- library / device ---------------------------------------------------- */
+int spy_abi_version(void);
+/* replaces utils.get_num_threads (utils.pyx:18-25): number of visible B200s */
+int spy_device_count(void);
+const char *spy_last_error(void);
+
+/*
+ * Arguments of the similarity kernel.  Field for field this is the parameter
+ * list of s_plus::compute_similarities_parallel<int,float> (s_plus.h:265-304,
+ * call site s_plus.pyx:359-384) minus the progress bar / thread count, plus the
+ * launch plan the GPU needs (panel split points) and an explicit per-row count.
+ */
+typedef struct spy_knn_args {
+    /* target rows: n_targets row ids of A (s_plus.h:267-268) */
+    int32_t n_targets;
+    const int32_t *targets;
+    /* A = matrix1 in CSR (s_plus.h:269-271) */
+    int32_t a_rows;
+    const int32_t *a_indptr;
+    const int32_t *a_indices;
+    const float *a_data;
+    /* B = matrix2 in CSR, n_output_cols columns (s_plus.h:272-274, 291).
+     * When n_panels > 1 the column indices inside every row must be ascending
+     * (same requirement as the reference's blocked path, s_plus.h:381-394). */
+    int32_t b_rows;
+    int32_t n_cols;
+    const int32_t *b_indptr;
+    const int32_t *b_indices;
+    const float *b_data;
+    /* similarity terms (s_plus.h:275-289); a vector may be NULL when its weight is 0 */
+    const float *Xtversky, *Ytversky;
+    const float *Xcosine, *Ycosine;
+    const float *Xdepop, *Ydepop;
+    float a1, l1, l2, l3, t1, t2;
+    float stabilized_shrink, bayesian_shrink, threshold;
+    int32_t k;
+    /* per-row column selectors (s_plus.h:292-297): CSR index arrays with sorted rows,
+     * indexed by the TARGET ROW ID.  SPY_SEL_ARRAY is treated like NONE (the caller
+     * pre-filters B, s_plus.pyx:290-295). */
+    int32_t filter_mode;
+    const int32_t *filter_indptr, *filter_indices;
+    int32_t target_mode;
+    const int32_t *target_indptr, *target_indices;
+    /* outputs: slab of n_targets*k entries, row i owns [k*i, k*i+k) (s_plus.h:298-300,443-450).
+     * Entries are written best-first (value descending, ties by ascending column);
+     * the tail of a short row is zero-filled, so the slab never needs a memset.
+     * out_rows may be NULL (rows are implied by the slab position); out_counts may be NULL. */
+    int32_t *out_rows;
+    int32_t *out_cols;
+    float *out_values;
+    int32_t *out_counts;
+    /* launch plan -- zero means "let the library choose" */
+    int32_t panel_width;        /* accumulator columns per pass (multiple of 128)          */
+    const int32_t *b_split;     /* [b_rows * split_stride] from spy_knn_build_split_dev     */
+    int32_t split_stride;
+    int32_t n_panels;
+    int32_t threads;            /* 256, 512 or 1024                                         */
+    int32_t lanes_per_segment;  /* 4, 8, 16 or 32                                           */
+    const int32_t *row_order;   /* optional permutation of [0,n_targets): processing order  */
+} spy_knn_args;
+
+/* Choose panel_width / n_panels / split_stride / threads / lanes for a problem.
+ * avg_b_row_nnz only steers lanes_per_segment.  Fills the plan fields of *args. */
+int spy_knn_plan(spy_knn_args *args, double avg_b_row_nnz, int device);
+
+/* Bytes of device scratch spy_knn_topk_dev needs for *args (after spy_knn_plan). */
+int64_t spy_knn_scratch_bytes(const spy_knn_args *args, int device);
+
+/* Panel split points of B: split[u*stride + p] = first position q in row u with
+ * b_indices[q] >= p*panel_width (p = 0..n_panels).  Replaces the per-(row,block)
+ * std::lower_bound calls of the blocked path (s_plus.h:381-394) by one pass over B. */
+int spy_knn_build_split_dev(int32_t b_rows, const int32_t *b_indptr, const int32_t *b_indices,
+                            int32_t panel_width, int32_t n_panels, int32_t split_stride,
+                            int32_t *split_out, void *stream);
+
+/* The hot path.  Replaces s_plus::compute_similarities_parallel<int,float>
+ * (s_plus.h:265-453).  Device pointers; scratch is spy_knn_scratch_bytes() bytes. */
+int spy_knn_topk_dev(const spy_knn_args *args, void *scratch, int64_t scratch_bytes, void *stream);
+
+/* Same contract with HOST pointers (exactly what the reference's Cython call site holds,
+ * s_plus.pyx:359-384): uploads, plans, runs, downloads.  out_rows/out_cols/out_values are
+ * host arrays of n_targets*k entries. */
+int spy_knn_topk_host(const spy_knn_args *host_args, int device);
+
+/* Kernel launches performed by the calling thread since the last call (diagnostics / bench). */
+int64_t spy_launch_count(int reset);
+
+/* ---- pre-processing on CSR (device pointers) ------------------------------ */
+/* csr_sum axis=1 (s_plus_utils.pyx:151-159): out[r] = sum data (or data^2) of row r, fp32 */
+int spy_csr_row_sum_dev(int32_t n_rows, const int32_t *indptr, const float *data, int square,
+                        float *out, void *stream);
+/* csr_sum axis=0 (s_plus_utils.pyx:160-164): fp64 accumulation, cast to fp32.
+ * acc64 is n_cols doubles of scratch. */
+int spy_csr_col_sum_dev(int64_t nnz, const int32_t *indices, const float *data, int square,
+                        int32_t n_cols, double *acc64, float *out, void *stream);
+/* np.power(x + shift, p, dtype=float32) (s_plus_utils.pyx:226-227, 258-274); x may be f32 or f64 */
+int spy_pow_shift_dev(int64_t n, const void *x, int x_dtype, float shift, float p, float *out, void *stream);
+/* column histogram of a CSR (used by transpose and by array-mode filtering) */
+int spy_csr_col_count_dev(int64_t nnz, const int32_t *indices, int32_t n_cols, int32_t *counts, void *stream);
+/* exclusive scan of int32 counts into int32 offsets of length n+1 (n <= 2^31-2); tmp = spy_scan_tmp_bytes(n) */
+int64_t spy_scan_tmp_bytes(int64_t n);
+int spy_exclusive_scan_i32_dev(int64_t n, const int32_t *counts, int32_t *offsets, void *tmp, void *stream);
+int spy_exclusive_scan_i64_dev(int64_t n, const int32_t *counts, int64_t *offsets, void *tmp, void *stream);
+/* CSR -> CSC (== transpose in CSR) with ascending indices in every output row.
+ * Replaces scipy's csr_tocsc behind matrix1.T.tocsr() (s_plus.pyx:170,205-206).
+ * t_indptr must already hold the exclusive scan of the column counts (n_cols+1);
+ * cursor is n_cols int32 of scratch. */
+int spy_csr_transpose_dev(int32_t n_rows, int32_t n_cols, const int32_t *indptr, const int32_t *indices,
+                          const float *data, const int32_t *t_indptr, int32_t *t_indices, float *t_data,
+                          int32_t *cursor, void *stream);
+/* sort_indices (s_plus_utils.pyx:344,573): ascending column ids inside every row, in place */
+int spy_csr_sort_rows_dev(int32_t n_rows, const int32_t *indptr, int32_t *indices, float *data, void *stream);
+/* keep[i] != 0 entries only (eliminate_zeros s_plus.pyx:210-211 with keep = data != 0;
+ * _filter_matrix_columns s_plus_utils.pyx:424-490 with keep = mask[indices]).
+ * Two calls: count (fills row_counts), then -- after the caller scanned them -- compact. */
+int spy_csr_filter_count_dev(int32_t n_rows, const int32_t *indptr, const int32_t *indices, const float *data,
+                             const uint8_t *col_mask, int drop_zeros, int32_t *row_counts, void *stream);
+int spy_csr_filter_compact_dev(int32_t n_rows, const int32_t *indptr, const int32_t *indices, const float *data,
+                               const uint8_t *col_mask, int drop_zeros, const int32_t *new_indptr,
+                               int32_t *new_indices, float *new_data, void *stream);
+/* dtype conversion of values: binary => ones (s_plus_utils.pyx:281-308) */
+int spy_cast_values_dev(int64_t n, const void *src, int src_dtype, int binary, float *dst, void *stream);
+
+/* ---- output assembly (device pointers) ------------------------------------- */
+/* Slab -> CSR with explicit zeros removed: replaces build_csr_matrix + coo_to_csr +
+ * eliminate_zeros (utils.pyx:67-173, coo_to_csr.h:28-71, s_plus.pyx:424).
+ *   1. spy_slab_row_nnz_dev: row_nnz[targets[i]] = #entries with value != 0 among the first
+ *      counts[i] of slab row i (row_nnz has one int per OUTPUT row and must be zeroed first;
+ *      target rows must be unique -- duplicates are assembled by the host wrapper);
+ *   2. the caller scans row_nnz into csr_indptr (spy_exclusive_scan_i64_dev);
+ *   3. spy_slab_compact_dev writes the kept (col, value) pairs at csr_indptr[targets[i]].
+ * idx_dtype selects int32 / int64 csr_indices (get_index_dtype, utils.pyx:28-40). */
+int spy_slab_row_nnz_dev(int32_t n_targets, int32_t k, const float *values, const int32_t *counts,
+                         const int32_t *targets, int32_t *row_nnz, void *stream);
+int spy_slab_compact_dev(int32_t n_targets, int32_t k, const int32_t *cols, const float *values,
+                         const int32_t *counts, const int32_t *targets, const int64_t *csr_indptr,
+                         void *csr_indices, int idx_dtype, float *csr_data, void *stream);
+/* COO rows for the slab exactly as the reference leaves them (s_plus.h:443-450,
+ * s_plus.pyx:351-353): rows[i*k+j] = targets[i] for j < counts[i], else 0. */
+int spy_slab_fill_rows_dev(int32_t n_targets, int32_t k, const int32_t *targets, const int32_t *counts,
+                           int32_t *rows, void *stream);
+
+/* ---- in-place CSR normalizers (device pointers) --------------------------- */
+/* inplace_normalize_csr_{l1,l2,max} (normalization.pyx:97-197); norm: 0=l1 1=l2 2=max */
+int spy_normalize_rows_dev(int norm, int64_t n_rows, void *data, int val_dtype, const void *indptr,
+                           int idx_dtype, void *stream);
+/* inplace_normalize_csr_tfidf (normalization.pyx:200-257).
+ * scratch: spy_tfidf_scratch_bytes(n_rows, n_cols, val_dtype) bytes. */
+int64_t spy_tfidf_scratch_bytes(int64_t n_rows, int64_t n_cols, int val_dtype);
+int spy_tfidf_dev(int64_t n_rows, int64_t n_cols, void *data, int val_dtype, const void *indices,
+                  const void *indptr, int idx_dtype, int tf_mode, int idf_mode, double logbase,
+                  void *scratch, void *stream);
+/* inplace_normalize_csr_bm25plus (normalization.pyx:260-334); bm25 == delta 0 */
+int spy_bm25plus_dev(int64_t n_rows, int64_t n_cols, void *data, int val_dtype, const void *indices,
+                     const void *indptr, int idx_dtype, double k1, double b, double delta,
+                     int tf_mode, int idf_mode, double logbase, void *scratch, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIMILARIPY_B200_H_ */

@@ -1,0 +1,535 @@
+"""Host driver of the B200 similarity path: the Python mirror of the reference's Cython glue
+``similaripy/cython_code/s_plus.pyx:95-433`` (validate -> CSR -> norm vectors -> selectors ->
+kernel -> output matrix), with every O(nnz) step running as a CUDA kernel behind the C ABI
+(``include/similaripy_b200.h``).  PyTorch is used only for device memory, streams and copies.
+
+There is no CPU fallback: without the CUDA library or without a GPU the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+import scipy.sparse as sp
+
+from . import _lib
+
+MODE_NONE, MODE_ARRAY, MODE_MATRIX = _lib.SEL_NONE, _lib.SEL_ARRAY, _lib.SEL_MATRIX
+INT32_MAX = np.iinfo(np.int32).max
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def resolve_device(device=None):
+    """Device the call runs on: explicit argument, else $SIMILARIPY_B200_DEVICE, else the current CUDA device."""
+    torch = _torch()
+    if not torch.cuda.is_available():
+        raise RuntimeError("similaripy_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    if device is None:
+        env = os.environ.get("SIMILARIPY_B200_DEVICE")
+        device = int(env) if env not in (None, "") else torch.cuda.current_device()
+    if isinstance(device, int):
+        return torch.device("cuda", device)
+    return torch.device(device)
+
+
+def _ptr(t) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class Ctx:
+    """Device + stream + the loaded C library for one call."""
+
+    def __init__(self, device=None):
+        torch = _torch()
+        self.torch = torch
+        self.lib = _lib.load()
+        self.device = resolve_device(device)
+        self.index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        torch.cuda.set_device(self.index)
+        self.stream = torch.cuda.current_stream(self.device)
+        self.sptr = C.c_void_p(self.stream.cuda_stream)
+
+    # -- memory helpers ---------------------------------------------------------------------
+    def empty(self, n, dtype):
+        return self.torch.empty(int(n), dtype=dtype, device=self.device)
+
+    def zeros(self, n, dtype):
+        return self.torch.zeros(int(n), dtype=dtype, device=self.device)
+
+    def h2d(self, arr: np.ndarray):
+        arr = np.ascontiguousarray(arr)
+        if not arr.flags.writeable:
+            arr = arr.copy()
+        # pinned host memory (is_pinned) makes this a true async DMA; pageable memory is staged by torch
+        return self.torch.from_numpy(arr).to(self.device, non_blocking=True)
+
+    def d2h(self, t) -> np.ndarray:
+        host = self.torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        host.copy_(t, non_blocking=True)
+        return host
+
+    def sync(self):
+        self.stream.synchronize()
+
+    # -- small kernels ----------------------------------------------------------------------
+    def scan_i32(self, counts):
+        n = counts.numel()
+        out = self.empty(n + 1, self.torch.int32)
+        tmp = self.empty(self.lib.spy_scan_tmp_bytes(n), self.torch.uint8)
+        _lib.check(self.lib.spy_exclusive_scan_i32_dev(n, _ptr(counts), _ptr(out), _ptr(tmp), self.sptr))
+        return out
+
+    def scan_i64(self, counts):
+        n = counts.numel()
+        out = self.empty(n + 1, self.torch.int64)
+        tmp = self.empty(self.lib.spy_scan_tmp_bytes(n), self.torch.uint8)
+        _lib.check(self.lib.spy_exclusive_scan_i64_dev(n, _ptr(counts), _ptr(out), _ptr(tmp), self.sptr))
+        return out
+
+
+@dataclass
+class DeviceCSR:
+    """A CSR matrix resident in HBM: int32 indptr/indices, float32 data."""
+    n_rows: int
+    n_cols: int
+    indptr: object
+    indices: object
+    data: object
+    sorted_rows: bool = False
+
+    @property
+    def nnz(self) -> int:
+        return int(self.indices.numel())
+
+
+_VAL_CODES = {np.dtype(np.float32): _lib.F32, np.dtype(np.float64): _lib.F64,
+              np.dtype(np.int32): _lib.VAL_I32, np.dtype(np.int64): _lib.VAL_I64}
+
+
+def _upload_values(ctx: Ctx, data: np.ndarray, binary: bool):
+    """matrix.data.astype(float32) / ones for binary (s_plus_utils.pyx:281-308) on the device."""
+    torch = ctx.torch
+    n = data.shape[0]
+    if binary:
+        out = ctx.empty(n, torch.float32)
+        _lib.check(ctx.lib.spy_cast_values_dev(n, _ptr(out), _lib.F32, 1, _ptr(out), ctx.sptr))
+        return out
+    dt = np.dtype(data.dtype)
+    if dt == np.float32:
+        return ctx.h2d(data)
+    if dt not in _VAL_CODES:
+        return ctx.h2d(data.astype(np.float32))
+    raw = ctx.h2d(data)
+    out = ctx.empty(n, torch.float32)
+    _lib.check(ctx.lib.spy_cast_values_dev(n, _ptr(raw), _VAL_CODES[dt], 0, _ptr(out), ctx.sptr))
+    return out
+
+
+def _upload_index(ctx: Ctx, arr: np.ndarray):
+    if arr.dtype != np.int32:
+        arr = arr.astype(np.int32)  # s_plus.pyx:241-244
+    return ctx.h2d(arr)
+
+
+def transpose_csr(ctx: Ctx, m: DeviceCSR) -> DeviceCSR:
+    """CSR -> CSR of the transpose, rows sorted (scipy csr_tocsc behind s_plus.pyx:205-206)."""
+    torch = ctx.torch
+    counts = ctx.empty(max(m.n_cols, 1), torch.int32)[: m.n_cols]
+    _lib.check(ctx.lib.spy_csr_col_count_dev(m.nnz, _ptr(m.indices), m.n_cols, _ptr(counts), ctx.sptr))
+    t_indptr = ctx.scan_i32(counts)
+    t_indices = ctx.empty(m.nnz, torch.int32)
+    t_data = ctx.empty(m.nnz, torch.float32)
+    cursor = ctx.empty(max(m.n_cols, 1), torch.int32)
+    _lib.check(ctx.lib.spy_csr_transpose_dev(m.n_rows, m.n_cols, _ptr(m.indptr), _ptr(m.indices), _ptr(m.data),
+                                             _ptr(t_indptr), _ptr(t_indices), _ptr(t_data), _ptr(cursor), ctx.sptr))
+    return DeviceCSR(m.n_cols, m.n_rows, t_indptr, t_indices, t_data, sorted_rows=True)
+
+
+def filter_csr(ctx: Ctx, m: DeviceCSR, col_mask=None, drop_zeros=False, values=None) -> DeviceCSR:
+    """Keep entries with mask[col] != 0 and/or value != 0; returns m itself when nothing is dropped."""
+    torch = ctx.torch
+    data = m.data if values is None else values
+    counts = ctx.empty(max(m.n_rows, 1), torch.int32)[: m.n_rows]
+    _lib.check(ctx.lib.spy_csr_filter_count_dev(m.n_rows, _ptr(m.indptr), _ptr(m.indices), _ptr(data),
+                                                _ptr(col_mask), 1 if drop_zeros else 0, _ptr(counts), ctx.sptr))
+    new_indptr = ctx.scan_i32(counts)
+    kept = int(new_indptr[-1].item()) if m.n_rows > 0 else 0
+    if kept == m.nnz and values is None:
+        return m
+    new_indices = ctx.empty(kept, torch.int32)
+    new_data = ctx.empty(kept, torch.float32)
+    _lib.check(ctx.lib.spy_csr_filter_compact_dev(m.n_rows, _ptr(m.indptr), _ptr(m.indices), _ptr(data),
+                                                  _ptr(col_mask), 1 if drop_zeros else 0, _ptr(new_indptr),
+                                                  _ptr(new_indices), _ptr(new_data), ctx.sptr))
+    return DeviceCSR(m.n_rows, m.n_cols, new_indptr, new_indices, new_data, sorted_rows=m.sorted_rows)
+
+
+def upload_stored(ctx: Ctx, matrix):
+    """Upload a scipy sparse matrix in its STORED orientation, zero-free, values as float32.
+
+    Returns (DeviceCSR over the stored major axis, transposed_flag): a CSR matrix is uploaded as is
+    (flag False); a CSC matrix -- what ``X.T`` of a CSR is -- is uploaded as the CSR of its transpose
+    (flag True) without any host-side conversion; other formats go through scipy's ``tocsr`` first.
+    Covers s_plus.pyx:205-211 (tocsr + eliminate_zeros) and :237-244 (float32 / int32 views).
+    """
+    fmt = getattr(matrix, "format", None)
+    if fmt not in ("csr", "csc"):
+        matrix = matrix.tocsr()
+        fmt = "csr"
+    major, minor = (matrix.shape if fmt == "csr" else matrix.shape[::-1])
+    if max(matrix.shape) > INT32_MAX or matrix.nnz > INT32_MAX:
+        raise ValueError("matrix dimensions / nnz exceed int32, which the similarity kernel (like the reference) uses")
+    m = DeviceCSR(major, minor, _upload_index(ctx, matrix.indptr), _upload_index(ctx, matrix.indices),
+                  _upload_values(ctx, matrix.data, binary=False),
+                  sorted_rows=bool(getattr(matrix, "_has_sorted_indices", False)))
+    before = m.nnz
+    m = filter_csr(ctx, m, drop_zeros=True)  # eliminate_zeros (s_plus.pyx:210-211)
+    if m.nnz != before and fmt == "csr":
+        matrix.eliminate_zeros()  # the reference mutates a CSR argument in place; keep that side effect
+    return m, fmt == "csc"
+
+
+def binarize(ctx: Ctx, m: DeviceCSR) -> DeviceCSR:
+    """binary=True: every stored value becomes 1.0 (s_plus_utils.pyx:301-304)."""
+    ones = ctx.empty(m.nnz, ctx.torch.float32)
+    _lib.check(ctx.lib.spy_cast_values_dev(m.nnz, _ptr(ones), _lib.F32, 1, _ptr(ones), ctx.sptr))
+    return DeviceCSR(m.n_rows, m.n_cols, m.indptr, m.indices, ones, sorted_rows=m.sorted_rows)
+
+
+def upload_pair(ctx: Ctx, matrix1, matrix2):
+    """A = matrix1 and B = matrix2 as device CSR.  With matrix2=None (B = matrix1.T, s_plus.pyx:169-170)
+    the data crosses PCIe once and is transposed once on the GPU, whichever of CSR / CSC matrix1 is."""
+    s1, t1 = upload_stored(ctx, matrix1)
+    if matrix2 is None:
+        other = transpose_csr(ctx, s1)
+        return (other, s1) if t1 else (s1, other)
+    A = transpose_csr(ctx, s1) if t1 else s1
+    s2, t2 = upload_stored(ctx, matrix2)
+    B = transpose_csr(ctx, s2) if t2 else s2
+    return A, B
+
+
+# --------------------------------------------------------------------------------------------
+# validation (s_plus_utils.pyx:19-125): same checks, same exception types, same order
+# --------------------------------------------------------------------------------------------
+def validate_inputs(matrix1, matrix2, weight_depop_matrix1, weight_depop_matrix2, k, target_rows,
+                    filter_cols, target_cols, verbose, format_output) -> None:
+    if not sp.issparse(matrix1):
+        raise TypeError("matrix1 must be a sparse matrix")
+    if not sp.issparse(matrix2):
+        raise TypeError("matrix2 must be a sparse matrix")
+    if matrix1.shape[1] != matrix2.shape[0]:
+        raise ValueError(f"Incompatible matrix shapes: matrix1.shape[1]={matrix1.shape[1]} "
+                         f"must equal matrix2.shape[0]={matrix2.shape[0]}")
+    if k < 1:
+        raise ValueError(f"k must be >= 1, got {k}")
+    for name, w, n in (("weight_depop_matrix1", weight_depop_matrix1, matrix1.shape[0]),
+                       ("weight_depop_matrix2", weight_depop_matrix2, matrix2.shape[1])):
+        if isinstance(w, str):
+            ok = w in ("none", "sum") or len(w) == n
+        else:
+            ok = len(w) == n
+        if not ok:
+            raise ValueError(f'{name} must be array of length {n} or one of ("none", "sum"), got length {len(w)}')
+    if target_rows is not None and len(target_rows) > matrix1.shape[0]:
+        raise ValueError(f"target_rows length ({len(target_rows)}) cannot exceed matrix1.shape[0] ({matrix1.shape[0]})")
+    for name, cols in (("filter_cols", filter_cols), ("target_cols", target_cols)):
+        if cols is None:
+            continue
+        if not (sp.issparse(cols) or isinstance(cols, (list, np.ndarray))):
+            raise TypeError(f"{name} must be a sparse matrix, list, numpy array, or None")
+        if sp.issparse(cols) and cols.data.shape[0] != 0:
+            expected = (matrix1.shape[0], matrix2.shape[1])
+            if cols.shape != expected:
+                raise ValueError(f"{name} shape {cols.shape} does not match expected shape {expected}")
+    if not isinstance(verbose, bool):
+        raise TypeError(f"verbose must be boolean, got {type(verbose).__name__}")
+    if format_output not in ("coo", "csr"):
+        raise ValueError(f"format_output must be 'coo' or 'csr', got '{format_output}'")
+
+
+def selector_mode(cols) -> int:
+    """s_plus_utils.pyx:311-361."""
+    if sp.issparse(cols) and cols.data.shape[0] != 0:
+        return MODE_MATRIX
+    if isinstance(cols, (list, np.ndarray)) and len(cols) != 0:
+        return MODE_ARRAY
+    return MODE_NONE
+
+
+def keep_mask(filter_cols, target_cols, n_cols: int) -> np.ndarray:
+    """List-mode column set target \\ filter, out-of-range ids dropped (s_plus_utils.pyx:364-421)."""
+    if selector_mode(target_cols) == MODE_ARRAY:
+        mask = np.zeros(n_cols, dtype=np.uint8)
+        t = np.asarray(target_cols, dtype=np.int32)
+        mask[t[(t >= 0) & (t < n_cols)]] = 1
+    else:
+        mask = np.ones(n_cols, dtype=np.uint8)
+    if selector_mode(filter_cols) == MODE_ARRAY:
+        f = np.asarray(filter_cols, dtype=np.int32)
+        mask[f[(f >= 0) & (f < n_cols)]] = 0
+    return mask
+
+
+@dataclass
+class KnnJob:
+    """Everything resident on the device for one similarity call."""
+    ctx: Ctx
+    A: DeviceCSR
+    B: DeviceCSR
+    targets: object
+    n_targets: int
+    k: int
+    n_rows: int
+    n_cols: int
+    params: dict
+    vectors: dict = field(default_factory=dict)
+    filter_mode: int = MODE_NONE
+    filter_m: tuple = (None, None)
+    target_mode: int = MODE_NONE
+    target_m: tuple = (None, None)
+    args: Optional[_lib.KnnArgs] = None
+    keep: list = field(default_factory=list)
+    out_cols: object = None
+    out_vals: object = None
+    out_counts: object = None
+    unique_targets: bool = True
+    tuning: dict = field(default_factory=dict)
+
+    # ---- norm vectors (s_plus.pyx:259-269) ------------------------------------------------
+    def build_vectors(self, weight_depop_matrix1, weight_depop_matrix2, p1, p2, c1, c2, additive_shrink):
+        ctx, lib, torch = self.ctx, self.ctx.lib, self.ctx.torch
+        A, B, P = self.A, self.B, self.params
+        v = {}
+        if P["l1"] != 0 or P["l2"] != 0:  # _build_squared_norms, s_plus_utils.pyx:169-201
+            sq1 = ctx.empty(A.n_rows, torch.float32)
+            _lib.check(lib.spy_csr_row_sum_dev(A.n_rows, _ptr(A.indptr), _ptr(A.data), 1, _ptr(sq1), ctx.sptr))
+            sq2 = ctx.empty(B.n_cols, torch.float32)
+            acc = ctx.empty(max(B.n_cols, 1), torch.float64)
+            _lib.check(lib.spy_csr_col_sum_dev(B.nnz, _ptr(B.indices), _ptr(B.data), 1, B.n_cols, _ptr(acc), _ptr(sq2), ctx.sptr))
+        if P["l1"] != 0:
+            v["Xt"], v["Yt"] = sq1, sq2
+        if P["l2"] != 0:  # _build_cosine_normalization, s_plus_utils.pyx:204-228
+            v["Xc"] = ctx.empty(A.n_rows, torch.float32)
+            v["Yc"] = ctx.empty(B.n_cols, torch.float32)
+            _lib.check(lib.spy_pow_shift_dev(A.n_rows, _ptr(sq1), _lib.F32, additive_shrink, c1, _ptr(v["Xc"]), ctx.sptr))
+            _lib.check(lib.spy_pow_shift_dev(B.n_cols, _ptr(sq2), _lib.F32, additive_shrink, c2, _ptr(v["Yc"]), ctx.sptr))
+        if P["l3"] != 0:  # _build_depop_normalization, s_plus_utils.pyx:231-278
+            v["Xd"] = self._depop(weight_depop_matrix1, p1, axis=1)
+            v["Yd"] = self._depop(weight_depop_matrix2, p2, axis=0)
+        self.vectors = v
+
+    def _depop(self, spec, p, axis):
+        ctx, lib, torch = self.ctx, self.ctx.lib, self.ctx.torch
+        m = self.A if axis == 1 else self.B
+        n = m.n_rows if axis == 1 else m.n_cols
+        out = ctx.empty(n, torch.float32)
+        if isinstance(spec, (list, np.ndarray)):
+            w = np.asarray(spec)
+            if w.dtype not in (np.float32, np.float64):
+                w = w.astype(np.float32)
+            wd = ctx.h2d(w.ravel())
+            code = _lib.F32 if w.dtype == np.float32 else _lib.F64
+            _lib.check(lib.spy_pow_shift_dev(n, _ptr(wd), code, 0.0, p, _ptr(out), ctx.sptr))
+            self.keep.append(wd)
+        elif spec == "none":
+            out.fill_(1.0)
+        elif spec == "sum":
+            s = ctx.empty(n, torch.float32)
+            if axis == 1:
+                _lib.check(lib.spy_csr_row_sum_dev(m.n_rows, _ptr(m.indptr), _ptr(m.data), 0, _ptr(s), ctx.sptr))
+            else:
+                acc = ctx.empty(max(n, 1), torch.float64)
+                _lib.check(lib.spy_csr_col_sum_dev(m.nnz, _ptr(m.indices), _ptr(m.data), 0, n, _ptr(acc), _ptr(s), ctx.sptr))
+            _lib.check(lib.spy_pow_shift_dev(n, _ptr(s), _lib.F32, 0.0, p, _ptr(out), ctx.sptr))
+        else:
+            raise ValueError(f"Invalid depopularization weights: {spec}")
+        return out
+
+    # ---- selectors (s_plus.pyx:284-295) -----------------------------------------------------
+    def build_selectors(self, filter_cols, target_cols, raw_b_values):
+        ctx = self.ctx
+        self.filter_mode = selector_mode(filter_cols)
+        self.target_mode = selector_mode(target_cols)
+        for which, cols, mode in (("filter_m", filter_cols, self.filter_mode), ("target_m", target_cols, self.target_mode)):
+            if mode == MODE_MATRIX:  # per-row lists, sorted for the in-kernel range search
+                c = cols.tocsr()
+                c.eliminate_zeros()
+                c.sort_indices()
+                setattr(self, which, (_upload_index(ctx, c.indptr), _upload_index(ctx, c.indices)))
+        if self.filter_mode == MODE_ARRAY or self.target_mode == MODE_ARRAY:
+            mask = ctx.h2d(keep_mask(filter_cols, target_cols, self.n_cols))
+            # the reference re-reads the restored (non-binary) values here: SURVEY 8a / a11
+            self.B = filter_csr(ctx, self.B, col_mask=mask, values=raw_b_values)
+            self.keep.append(mask)
+
+    # ---- plan + split points ------------------------------------------------------------------
+    def plan(self):
+        ctx, lib, torch = self.ctx, self.ctx.lib, self.ctx.torch
+        A, B, P, v = self.A, self.B, self.params, self.vectors
+        a = _lib.KnnArgs()
+        a.n_targets = self.n_targets
+        a.targets = _ptr(self.targets)
+        a.a_rows, a.a_indptr, a.a_indices, a.a_data = A.n_rows, _ptr(A.indptr), _ptr(A.indices), _ptr(A.data)
+        a.b_rows, a.n_cols = B.n_rows, self.n_cols
+        a.b_indptr, a.b_indices, a.b_data = _ptr(B.indptr), _ptr(B.indices), _ptr(B.data)
+        a.Xtversky, a.Ytversky = _ptr(v.get("Xt")), _ptr(v.get("Yt"))
+        a.Xcosine, a.Ycosine = _ptr(v.get("Xc")), _ptr(v.get("Yc"))
+        a.Xdepop, a.Ydepop = _ptr(v.get("Xd")), _ptr(v.get("Yd"))
+        for name in ("a1", "l1", "l2", "l3", "t1", "t2", "stabilized_shrink", "bayesian_shrink", "threshold"):
+            setattr(a, name, P[name])
+        a.k = self.k
+        a.filter_mode, a.filter_indptr, a.filter_indices = self.filter_mode, _ptr(self.filter_m[0]), _ptr(self.filter_m[1])
+        a.target_mode, a.target_indptr, a.target_indices = self.target_mode, _ptr(self.target_m[0]), _ptr(self.target_m[1])
+        a.threads = int(self.tuning.get("threads", 0))
+        a.lanes_per_segment = int(self.tuning.get("lanes", 0))
+        a.panel_width = int(self.tuning.get("panel_width", 0))
+        avg = (B.nnz / B.n_rows) if B.n_rows > 0 else 0.0
+        _lib.check(lib.spy_knn_plan(C.byref(a), avg, ctx.index))
+        if a.n_panels > 1:
+            if not B.sorted_rows:  # the panel split needs ascending columns inside every row of B
+                _lib.check(lib.spy_csr_sort_rows_dev(B.n_rows, _ptr(B.indptr), _ptr(B.indices), _ptr(B.data), ctx.sptr))
+                B.sorted_rows = True
+            split = ctx.empty(B.n_rows * a.split_stride, torch.int32)
+            _lib.check(lib.spy_knn_build_split_dev(B.n_rows, _ptr(B.indptr), _ptr(B.indices), a.panel_width, a.n_panels,
+                                                   a.split_stride, _ptr(split), ctx.sptr))
+            a.b_split = _ptr(split)
+            self.keep.append(split)
+        slab = self.n_targets * self.k
+        self.out_cols = ctx.empty(slab, torch.int32)
+        self.out_vals = ctx.empty(slab, torch.float32)
+        self.out_counts = ctx.empty(max(self.n_targets, 1), torch.int32)
+        a.out_rows = None
+        a.out_cols, a.out_values, a.out_counts = _ptr(self.out_cols), _ptr(self.out_vals), _ptr(self.out_counts)
+        sb = int(lib.spy_knn_scratch_bytes(C.byref(a), ctx.index))
+        if sb < 0:
+            _lib.check(sb)
+        self.scratch = ctx.empty(sb, torch.uint8)
+        self.scratch_bytes = sb
+        self.args = a
+
+    # ---- the hot kernel ---------------------------------------------------------------------------
+    def run(self):
+        _lib.check(self.ctx.lib.spy_knn_topk_dev(C.byref(self.args), _ptr(self.scratch), self.scratch_bytes, self.ctx.sptr))
+
+    # ---- output (s_plus.pyx:405-424) --------------------------------------------------------------
+    def assemble_device(self, format_output):
+        """Device part of the output assembly; returns device tensors ready for the D2H copy."""
+        ctx, lib, torch = self.ctx, self.ctx.lib, self.ctx.torch
+        k, nt = self.k, self.n_targets
+        if format_output == "coo":
+            rows = ctx.empty(nt * k, torch.int32)
+            _lib.check(lib.spy_slab_fill_rows_dev(nt, k, _ptr(self.targets), _ptr(self.out_counts), _ptr(rows), ctx.sptr))
+            return ("coo", rows, self.out_cols, self.out_vals)
+        if not self.unique_targets:
+            return ("slab", self.out_cols, self.out_vals, self.out_counts)
+        row_nnz = ctx.zeros(max(self.n_rows, 1), torch.int32)[: self.n_rows]
+        _lib.check(lib.spy_slab_row_nnz_dev(nt, k, _ptr(self.out_vals), _ptr(self.out_counts), _ptr(self.targets),
+                                            _ptr(row_nnz), ctx.sptr))
+        indptr = ctx.scan_i64(row_nnz)
+        nnz = int(indptr[-1].item())
+        # get_index_dtype(max(len(values), n_cols)) on the PADDED slab length, utils.pyx:165-168
+        idx64 = max(nt * k, self.n_cols) > INT32_MAX
+        indices = ctx.empty(nnz, torch.int64 if idx64 else torch.int32)
+        data = ctx.empty(nnz, torch.float32)
+        _lib.check(lib.spy_slab_compact_dev(nt, k, _ptr(self.out_cols), _ptr(self.out_vals), _ptr(self.out_counts),
+                                            _ptr(self.targets), _ptr(indptr), _ptr(indices),
+                                            _lib.I64 if idx64 else _lib.I32, _ptr(data), ctx.sptr))
+        if not idx64:
+            indptr = indptr.to(torch.int32)
+        return ("csr", indptr, indices, data)
+
+    def to_host(self, assembled):
+        ctx = self.ctx
+        kind = assembled[0]
+        shape = (self.n_rows, self.n_cols)
+        host = [ctx.d2h(t) for t in assembled[1:]]
+        ctx.sync()
+        host = [h.numpy() for h in host]
+        if kind == "coo":
+            rows, cols, vals = host
+            return sp.coo_array((vals, (rows, cols)), shape=shape, dtype=np.float32)
+        if kind == "csr":
+            indptr, indices, data = host
+            return sp.csr_array((data, indices, indptr), shape=shape, dtype=np.float32)
+        # duplicate target rows: stable counting sort by row on the host, duplicates carried over
+        cols, vals, counts = host
+        k = self.k
+        targets = self.targets.cpu().numpy()
+        valid = (np.arange(k, dtype=np.int64)[None, :] < counts[: self.n_targets, None]).ravel()
+        rows = np.repeat(targets, k)[valid]
+        cols, vals = cols[valid], vals[valid]
+        nz = vals != 0
+        rows, cols, vals = rows[nz], cols[nz], vals[nz]
+        order = np.argsort(rows, kind="stable")
+        indptr = np.zeros(self.n_rows + 1, dtype=np.int64)
+        np.cumsum(np.bincount(rows, minlength=self.n_rows), out=indptr[1:])
+        idx_dtype = np.int64 if max(self.n_targets * k, self.n_cols) > INT32_MAX else np.int32
+        return sp.csr_array((vals[order], cols[order].astype(idx_dtype), indptr.astype(idx_dtype)), shape=shape, dtype=np.float32)
+
+
+def prepare_job(matrix1, matrix2=None, weight_depop_matrix1="none", weight_depop_matrix2="none",
+                p1=0.0, p2=0.0, a1=1.0, l1=0.0, l2=0.0, l3=0.0, t1=1.0, t2=1.0, c1=0.5, c2=0.5, k=100,
+                stabilized_shrink=0.0, bayesian_shrink=0.0, additive_shrink=0.0, threshold=0.0, binary=False,
+                target_rows=None, filter_cols=None, target_cols=None, verbose=True, format_output="csr",
+                num_threads=0, block_size=0, device=None, tuning=None) -> KnnJob:
+    """Validate, upload and pre-process: everything up to (not including) the hot kernel."""
+    matrix2_given = matrix2
+    if matrix2 is None:  # s_plus.pyx:169-170
+        matrix2 = matrix1.T if sp.issparse(matrix1) else None
+    validate_inputs(matrix1, matrix2, weight_depop_matrix1, weight_depop_matrix2, k, target_rows,
+                    filter_cols, target_cols, verbose, format_output)
+    k = int(min(k, matrix2.shape[1]))  # s_plus.pyx:187-188
+    n_rows, n_cols = int(matrix1.shape[0]), int(matrix2.shape[1])
+    if target_rows is None:  # s_plus.pyx:191-196
+        targets_np = np.arange(n_rows, dtype=np.int32)
+        unique = True
+    else:
+        targets_np = np.ascontiguousarray(np.asarray(target_rows, dtype=np.int32))
+        unique = np.unique(targets_np).shape[0] == targets_np.shape[0]
+        if targets_np.size and (targets_np.min() < 0 or targets_np.max() >= n_rows):
+            # undefined behaviour in the reference (no bounds check, s_plus.h:344-346); refuse instead
+            raise ValueError(f"target_rows must lie in [0, {n_rows})")
+    ctx = Ctx(device)
+    array_mode = selector_mode(filter_cols) == MODE_ARRAY or selector_mode(target_cols) == MODE_ARRAY
+    A, B = upload_pair(ctx, matrix1, matrix2_given)
+    raw_b = B.data if (binary and array_mode) else None
+    if binary:
+        A, B = binarize(ctx, A), binarize(ctx, B)
+    f32 = lambda x: float(np.float32(x))
+    params = dict(a1=f32(a1), l1=f32(l1), l2=f32(l2), l3=f32(l3), t1=f32(t1), t2=f32(t2),
+                  stabilized_shrink=f32(stabilized_shrink), bayesian_shrink=f32(bayesian_shrink), threshold=f32(threshold))
+    job = KnnJob(ctx=ctx, A=A, B=B, targets=ctx.h2d(targets_np), n_targets=int(targets_np.shape[0]), k=k,
+                 n_rows=n_rows, n_cols=n_cols, params=params, unique_targets=unique, tuning=dict(tuning or {}))
+    job.build_vectors(weight_depop_matrix1, weight_depop_matrix2, f32(p1), f32(p2), f32(c1), f32(c2), f32(additive_shrink))
+    job.build_selectors(filter_cols, target_cols, raw_b)
+    job.plan()
+    return job
+
+
+def s_plus(matrix1, matrix2=None, weight_depop_matrix1="none", weight_depop_matrix2="none",
+           p1=0.0, p2=0.0, a1=1.0, l1=0.0, l2=0.0, l3=0.0, t1=1.0, t2=1.0, c1=0.5, c2=0.5, k=100,
+           stabilized_shrink=0.0, bayesian_shrink=0.0, additive_shrink=0.0, threshold=0.0, binary=False,
+           target_rows=None, filter_cols=None, target_cols=None, verbose=True, format_output="csr",
+           num_threads=0, block_size=0, device=None, tuning=None):
+    """Top-K similarity between the rows of matrix1 and the columns of matrix2.
+
+    Same arguments, defaults and result as the reference's ``cython_code.s_plus.s_plus``
+    (s_plus.pyx:95-123).  ``num_threads`` and ``block_size`` are accepted for compatibility: they
+    steer the reference's OpenMP team and CPU-cache blocking and have no meaning on the GPU
+    (the shared-memory panel width is planned by the library).  ``verbose`` is validated and ignored.
+    """
+    job = prepare_job(matrix1, matrix2, weight_depop_matrix1, weight_depop_matrix2, p1, p2, a1, l1, l2, l3, t1, t2,
+                      c1, c2, k, stabilized_shrink, bayesian_shrink, additive_shrink, threshold, binary,
+                      target_rows, filter_cols, target_cols, verbose, format_output, num_threads, block_size,
+                      device, tuning)
+    if job.n_targets > 0:
+        job.run()
+    return job.to_host(job.assemble_device(format_output))
