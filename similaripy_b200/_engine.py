@@ -17,6 +17,9 @@ import scipy.sparse as sp
 
 from . import _lib
 
+# When set to a list, every hot-kernel launch appends {start, end (CUDA events), plan...} to it (bench.py).
+KERNEL_TRACE = None
+
 MODE_NONE, MODE_ARRAY, MODE_MATRIX = _lib.SEL_NONE, _lib.SEL_ARRAY, _lib.SEL_MATRIX
 INT32_MAX = np.iinfo(np.int32).max
 
@@ -109,6 +112,38 @@ class DeviceCSR:
         return int(self.indices.numel())
 
 
+class DeviceMatrix:
+    """A sparse matrix resident in HBM, usable wherever the similarity functions take ``matrix1`` /
+    ``matrix2`` (chain calls without host round-trips).  ``stored`` is the CSR of the
+    matrix when ``transposed`` is False and the CSR of its transpose (== its CSC) when True, so ``.T``
+    is free, exactly like scipy's."""
+
+    def __init__(self, stored: DeviceCSR, transposed: bool):
+        self.stored = stored
+        self.transposed = bool(transposed)
+
+    @property
+    def shape(self):
+        s = self.stored
+        return (s.n_cols, s.n_rows) if self.transposed else (s.n_rows, s.n_cols)
+
+    @property
+    def nnz(self) -> int:
+        return self.stored.nnz
+
+    @property
+    def T(self) -> "DeviceMatrix":
+        return DeviceMatrix(self.stored, not self.transposed)
+
+    @property
+    def device(self):
+        return self.stored.indptr.device
+
+
+def _is_matrix(m) -> bool:
+    return sp.issparse(m) or isinstance(m, DeviceMatrix)
+
+
 _VAL_CODES = {np.dtype(np.float32): _lib.F32, np.dtype(np.float64): _lib.F64,
               np.dtype(np.int32): _lib.VAL_I32, np.dtype(np.int64): _lib.VAL_I64}
 
@@ -179,6 +214,10 @@ def upload_stored(ctx: Ctx, matrix):
     (flag True) without any host-side conversion; other formats go through scipy's ``tocsr`` first.
     Covers s_plus.pyx:205-211 (tocsr + eliminate_zeros) and :237-244 (float32 / int32 views).
     """
+    if isinstance(matrix, DeviceMatrix):
+        if matrix.device != ctx.device:
+            raise ValueError(f"DeviceMatrix lives on {matrix.device}, the call runs on {ctx.device}")
+        return matrix.stored, matrix.transposed
     fmt = getattr(matrix, "format", None)
     if fmt not in ("csr", "csc"):
         matrix = matrix.tocsr()
@@ -221,9 +260,9 @@ def upload_pair(ctx: Ctx, matrix1, matrix2):
 # --------------------------------------------------------------------------------------------
 def validate_inputs(matrix1, matrix2, weight_depop_matrix1, weight_depop_matrix2, k, target_rows,
                     filter_cols, target_cols, verbose, format_output) -> None:
-    if not sp.issparse(matrix1):
+    if not _is_matrix(matrix1):
         raise TypeError("matrix1 must be a sparse matrix")
-    if not sp.issparse(matrix2):
+    if not _is_matrix(matrix2):
         raise TypeError("matrix2 must be a sparse matrix")
     if matrix1.shape[1] != matrix2.shape[0]:
         raise ValueError(f"Incompatible matrix shapes: matrix1.shape[1]={matrix1.shape[1]} "
@@ -331,7 +370,15 @@ class KnnJob:
         m = self.A if axis == 1 else self.B
         n = m.n_rows if axis == 1 else m.n_cols
         out = ctx.empty(n, torch.float32)
-        if isinstance(spec, (list, np.ndarray)):
+        if ctx.torch.is_tensor(spec):  # already on the device (DeviceMatrix pipelines)
+            wd = spec.to(ctx.device)
+            if wd.dtype not in (torch.float32, torch.float64):
+                wd = wd.to(torch.float32)
+            wd = wd.contiguous().reshape(-1)
+            code = _lib.F32 if wd.dtype == torch.float32 else _lib.F64
+            _lib.check(lib.spy_pow_shift_dev(n, _ptr(wd), code, 0.0, p, _ptr(out), ctx.sptr))
+            self.keep.append(wd)
+        elif isinstance(spec, (list, np.ndarray)):
             w = np.asarray(spec)
             if w.dtype not in (np.float32, np.float64):
                 w = w.astype(np.float32)
@@ -417,7 +464,17 @@ class KnnJob:
 
     # ---- the hot kernel ---------------------------------------------------------------------------
     def run(self):
+        trace = KERNEL_TRACE
+        if trace is not None:  # bench / profiling: CUDA events on the launching stream around the hot kernel only
+            ev0 = self.ctx.torch.cuda.Event(enable_timing=True)
+            ev1 = self.ctx.torch.cuda.Event(enable_timing=True)
+            ev0.record(self.ctx.stream)
         _lib.check(self.ctx.lib.spy_knn_topk_dev(C.byref(self.args), _ptr(self.scratch), self.scratch_bytes, self.ctx.sptr))
+        if trace is not None:
+            ev1.record(self.ctx.stream)
+            trace.append(dict(start=ev0, end=ev1, n_targets=self.n_targets, k=self.k, n_panels=int(self.args.n_panels),
+                              panel_width=int(self.args.panel_width), threads=int(self.args.threads),
+                              lanes=int(self.args.lanes_per_segment)))
 
     # ---- output (s_plus.pyx:405-424) --------------------------------------------------------------
     def assemble_device(self, format_output):
@@ -445,6 +502,19 @@ class KnnJob:
         if not idx64:
             indptr = indptr.to(torch.int32)
         return ("csr", indptr, indices, data)
+
+    def to_device_matrix(self) -> DeviceMatrix:
+        """The result as a CSR DeviceMatrix (zero-free, rows in best-first order, like format_output='csr')."""
+        if not self.unique_targets:
+            raise ValueError("on_device=True needs unique target_rows")
+        if self.n_targets == 0:
+            z = self.ctx.zeros(self.n_rows + 1, self.ctx.torch.int32)
+            e = self.ctx.empty(0, self.ctx.torch.int32)
+            return DeviceMatrix(DeviceCSR(self.n_rows, self.n_cols, z, e, self.ctx.empty(0, self.ctx.torch.float32)), False)
+        _, indptr, indices, data = self.assemble_device("csr")
+        if indices.dtype != self.ctx.torch.int32:
+            raise ValueError("result exceeds int32 indexing; fetch it with on_device=False")
+        return DeviceMatrix(DeviceCSR(self.n_rows, self.n_cols, indptr, indices, data, sorted_rows=False), False)
 
     def to_host(self, assembled):
         ctx = self.ctx
@@ -483,7 +553,7 @@ def prepare_job(matrix1, matrix2=None, weight_depop_matrix1="none", weight_depop
     """Validate, upload and pre-process: everything up to (not including) the hot kernel."""
     matrix2_given = matrix2
     if matrix2 is None:  # s_plus.pyx:169-170
-        matrix2 = matrix1.T if sp.issparse(matrix1) else None
+        matrix2 = matrix1.T if _is_matrix(matrix1) else None
     validate_inputs(matrix1, matrix2, weight_depop_matrix1, weight_depop_matrix2, k, target_rows,
                     filter_cols, target_cols, verbose, format_output)
     k = int(min(k, matrix2.shape[1]))  # s_plus.pyx:187-188
@@ -518,7 +588,7 @@ def s_plus(matrix1, matrix2=None, weight_depop_matrix1="none", weight_depop_matr
            p1=0.0, p2=0.0, a1=1.0, l1=0.0, l2=0.0, l3=0.0, t1=1.0, t2=1.0, c1=0.5, c2=0.5, k=100,
            stabilized_shrink=0.0, bayesian_shrink=0.0, additive_shrink=0.0, threshold=0.0, binary=False,
            target_rows=None, filter_cols=None, target_cols=None, verbose=True, format_output="csr",
-           num_threads=0, block_size=0, device=None, tuning=None):
+           num_threads=0, block_size=0, device=None, tuning=None, on_device=False):
     """Top-K similarity between the rows of matrix1 and the columns of matrix2.
 
     Same arguments, defaults and result as the reference's ``cython_code.s_plus.s_plus``
@@ -532,4 +602,52 @@ def s_plus(matrix1, matrix2=None, weight_depop_matrix1="none", weight_depop_matr
                       device, tuning)
     if job.n_targets > 0:
         job.run()
+    if on_device:
+        return job.to_device_matrix()
     return job.to_host(job.assemble_device(format_output))
+
+
+def to_device(matrix, device=None) -> DeviceMatrix:
+    """Upload a scipy sparse matrix once (zero-free, float32 values, int32 indices) and return a handle the
+    similarity functions accept in place of ``matrix1`` / ``matrix2``."""
+    if isinstance(matrix, DeviceMatrix):
+        return matrix
+    if not sp.issparse(matrix):
+        raise TypeError("matrix must be a sparse matrix")
+    ctx = Ctx(device)
+    stored, transposed = upload_stored(ctx, matrix)
+    ctx.sync()
+    return DeviceMatrix(stored, transposed)
+
+
+def axis_sum(m: DeviceMatrix, axis: int):
+    """``matrix.sum(axis)`` of a DeviceMatrix as a float32 device tensor (similarity.py:479)."""
+    ctx = Ctx(m.device)
+    torch, lib, s = ctx.torch, ctx.lib, m.stored
+    along_stored_rows = (axis == 1) != m.transposed  # summing over the stored minor axis
+    if along_stored_rows:
+        out = ctx.empty(s.n_rows, torch.float32)
+        _lib.check(lib.spy_csr_row_sum_dev(s.n_rows, _ptr(s.indptr), _ptr(s.data), 0, _ptr(out), ctx.sptr))
+    else:
+        out = ctx.empty(s.n_cols, torch.float32)
+        acc = ctx.empty(max(s.n_cols, 1), torch.float64)
+        _lib.check(lib.spy_csr_col_sum_dev(s.nnz, _ptr(s.indices), _ptr(s.data), 0, s.n_cols, _ptr(acc), _ptr(out), ctx.sptr))
+        ctx.sync()
+    return out
+
+
+def pow_values_(m: DeviceMatrix, p: float) -> DeviceMatrix:
+    """``m.data = m.data ** p`` in place on the device (similarity.py:411-415, 480-483)."""
+    ctx = Ctx(m.device)
+    d = m.stored.data
+    _lib.check(ctx.lib.spy_pow_shift_dev(d.numel(), _ptr(d), _lib.F32, 0.0, float(p), _ptr(d), ctx.sptr))
+    return m
+
+
+def to_host(m: DeviceMatrix):
+    """DeviceMatrix -> scipy csr_array (or csc_array when the handle is a transposed view)."""
+    s = m.stored
+    arrs = [t.cpu().numpy() for t in (s.data, s.indices, s.indptr)]
+    if m.transposed:
+        return sp.csc_array(tuple(arrs), shape=m.shape, dtype=np.float32)
+    return sp.csr_array(tuple(arrs), shape=m.shape, dtype=np.float32)

@@ -30,12 +30,24 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found: the similaripy_b200 CUDA library cannot be built")
 
 
+STAMP = LIB + ".stamp"  # hash of the sources the library was built from (mtimes do not survive the gpurun snapshot)
+
+
+def source_hash() -> str:
+    import hashlib
+    h = hashlib.sha256()
+    for d in [os.path.join(HERE, s) for s in SOURCES + HEADERS]:
+        with open(d, "rb") as f:
+            h.update(f.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
 def needs_build() -> bool:
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(STAMP):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(HERE, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
-    return any(os.path.getmtime(d) > t for d in deps)
+    with open(STAMP) as f:
+        return f.read().strip() != source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -67,6 +79,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if verbose:
         print(" ".join(cmd))
     subprocess.check_call(cmd)
+    with open(STAMP, "w") as f:
+        f.write(source_hash())
     return LIB
 
 

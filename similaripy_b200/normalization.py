@@ -13,7 +13,7 @@ import numpy as np
 import scipy.sparse as sps
 
 from . import _lib
-from ._engine import Ctx, _ptr
+from ._engine import Ctx, DeviceCSR, DeviceMatrix, _ptr, transpose_csr
 
 _NORMALIZATIONS = ("l1", "l2", "max")
 _TF_MODES = ("binary", "raw", "sqrt", "freq", "log")
@@ -84,10 +84,48 @@ class _DeviceRows:
             self.X.data = out.copy()
 
 
+def _device_rows(X: DeviceMatrix, axis: int, inplace: bool):
+    """DeviceMatrix counterpart of _prepare_csr: the CSR whose ROWS are to be normalised, with values that
+    may be overwritten.  Returns (ctx, csr, transposed_flag_of_result)."""
+    if axis not in (0, 1):
+        raise ValueError(f"axis must be 0 or 1, got {axis}")
+    ctx = Ctx(X.device)
+    want_transposed = (axis == 0)  # axis=0 normalises the rows of X.T
+    s = X.stored
+    if X.transposed != want_transposed:  # stored orientation is the other one: transpose on the device (a copy)
+        s = transpose_csr(ctx, s)
+    elif not inplace:
+        s = DeviceCSR(s.n_rows, s.n_cols, s.indptr, s.indices, s.data.clone(), sorted_rows=s.sorted_rows)
+    return ctx, s, want_transposed
+
+
+def _device_weighting(X: DeviceMatrix, axis, inplace, bm25_args, tf_mode, idf_mode, logbase):
+    _validate_modes(tf_mode, idf_mode)
+    ctx, s, flag = _device_rows(X, axis, inplace)
+    lib = ctx.lib
+    scratch = ctx.empty(lib.spy_tfidf_scratch_bytes(s.n_rows, s.n_cols, _lib.F32), ctx.torch.uint8)
+    tf, idf = _lib.TF_MODES[tf_mode], _lib.IDF_MODES[idf_mode]
+    if bm25_args is None:
+        _lib.check(lib.spy_tfidf_dev(s.n_rows, s.n_cols, _ptr(s.data), _lib.F32, _ptr(s.indices), _ptr(s.indptr),
+                                     _lib.I32, tf, idf, float(logbase), _ptr(scratch), ctx.sptr))
+    else:
+        k1, b, delta = bm25_args
+        _lib.check(lib.spy_bm25plus_dev(s.n_rows, s.n_cols, _ptr(s.data), _lib.F32, _ptr(s.indices), _ptr(s.indptr),
+                                        _lib.I32, float(k1), float(b), float(delta), tf, idf, float(logbase),
+                                        _ptr(scratch), ctx.sptr))
+    ctx.sync()  # scratch is released on return
+    return DeviceMatrix(s, flag)
+
+
 def normalize(X, norm: str = "l2", axis: int = 1, inplace: bool = False, *, device=None):
     """Row (axis=1) or column (axis=0) l1 / l2 / max normalisation (normalization.py:91-113)."""
     if norm not in _NORMALIZATIONS:
         raise ValueError(f"norm must be one of {_NORMALIZATIONS}, got '{norm}'")
+    if isinstance(X, DeviceMatrix):
+        ctx, s, flag = _device_rows(X, axis, inplace)
+        _lib.check(ctx.lib.spy_normalize_rows_dev(_NORMALIZATIONS.index(norm), s.n_rows, _ptr(s.data), _lib.F32,
+                                                  _ptr(s.indptr), _lib.I32, ctx.sptr))
+        return DeviceMatrix(s, flag)
     X = _prepare_csr(X, axis, inplace)
     d = _DeviceRows(X, device, need_indices=False)
     _lib.check(d.ctx.lib.spy_normalize_rows_dev(_NORMALIZATIONS.index(norm), X.shape[0], _ptr(d.data), d.val_code,
@@ -97,6 +135,8 @@ def normalize(X, norm: str = "l2", axis: int = 1, inplace: bool = False, *, devi
 
 
 def _weighting(X, axis, inplace, device, bm25_args, tf_mode, idf_mode, logbase):
+    if isinstance(X, DeviceMatrix):
+        return _device_weighting(X, axis, inplace, bm25_args, tf_mode, idf_mode, logbase)
     _validate_modes(tf_mode, idf_mode)
     X = _prepare_csr(X, axis, inplace)
     d = _DeviceRows(X, device, need_indices=True)
