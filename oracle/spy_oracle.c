@@ -46,41 +46,50 @@ static inline int item_less(hitem_t a, hitem_t b) {
 
 typedef struct { hitem_t *h; int size; int cap; } heap_t;
 
-static void heap_sift_up(heap_t *hp, int i) {
-    hitem_t x = hp->h[i];
-    while (i > 0) {
-        int p = (i - 1) >> 1;
-        if (!item_less(x, hp->h[p])) break;
-        hp->h[i] = hp->h[p];
-        i = p;
+/* The slab keeps the heap's ARRAY order (s_plus.h:443-450), so the oracle reproduces the array layout of
+ * std::push_heap / std::pop_heap as libstdc++ implements them (bottom-up variant: pop_heap walks the hole
+ * down to a leaf along the preferred children, then sifts the displaced last element up from there).
+ * comp = std::greater<pair>: comp(a, b) == item_less(b, a); the root is the minimum. */
+static void heap_push_up(hitem_t *h, int hole, int top, hitem_t value) {
+    int parent = (hole - 1) / 2;
+    while (hole > top && item_less(value, h[parent])) {   /* comp(h[parent], value) */
+        h[hole] = h[parent];
+        hole = parent;
+        parent = (hole - 1) / 2;
     }
-    hp->h[i] = x;
+    h[hole] = value;
 }
 
-static void heap_sift_down(heap_t *hp, int i) {
-    hitem_t x = hp->h[i];
-    int n = hp->size;
-    for (;;) {
-        int c = 2 * i + 1;
-        if (c >= n) break;
-        if (c + 1 < n && item_less(hp->h[c + 1], hp->h[c])) c++;
-        if (!item_less(hp->h[c], x)) break;
-        hp->h[i] = hp->h[c];
-        i = c;
+static void heap_adjust(hitem_t *h, int hole, int len, hitem_t value) {
+    const int top = hole;
+    int child = hole;
+    while (child < (len - 1) / 2) {
+        child = 2 * (child + 1);
+        if (item_less(h[child - 1], h[child])) child--;    /* comp(h[child], h[child-1]) */
+        h[hole] = h[child];
+        hole = child;
     }
-    hp->h[i] = x;
+    if ((len & 1) == 0 && child == (len - 2) / 2) {
+        child = 2 * (child + 1);
+        h[hole] = h[child - 1];
+        hole = child - 1;
+    }
+    heap_push_up(h, hole, top, value);
 }
 
 static inline void topk_offer(heap_t *hp, int32_t index, float score) {
-    if (hp->size < hp->cap) {
-        hp->h[hp->size].score = score;
-        hp->h[hp->size].index = index;
+    hitem_t x; x.score = score; x.index = index;
+    if (hp->size < hp->cap) {                               /* push_back + push_heap */
         hp->size++;
-        heap_sift_up(hp, hp->size - 1);
-    } else if (score > hp->h[0].score) {
-        hp->h[0].score = score;
-        hp->h[0].index = index;
-        heap_sift_down(hp, 0);
+        heap_push_up(hp->h, hp->size - 1, 0, x);
+    } else if (score > hp->h[0].score) {                    /* pop_heap; back() = x; push_heap */
+        int n = hp->size;
+        if (n > 1) {
+            hitem_t last = hp->h[n - 1];
+            hp->h[n - 1] = hp->h[0];
+            heap_adjust(hp->h, 0, n - 1, last);
+        }
+        heap_push_up(hp->h, n - 1, 0, x);
     }
 }
 

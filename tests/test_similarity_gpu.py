@@ -67,3 +67,157 @@ def test_binary_ties():
         ref, got = both(name, m, k=10, binary=True)
         stats = assert_topk_parity(ref, got, k=10, rtol=1e-6, what=f"binary {name}")
         assert stats["full_rows"] > 0
+
+
+# ---- selectors, edge cases, README flow (reference tests/test_similarity.py:359-617) ----------------------
+def test_readme_flow_bm25_cosine_recommend():
+    urm = sp.random_array((1000, 2000), density=0.025, format="csr", dtype=np.float32,
+                          random_state=np.random.default_rng(0))
+    w = sim.bm25(urm)
+    w_ref = oracle.bm25(urm)
+    np.testing.assert_allclose(w.data, w_ref.data, rtol=1e-5)
+    model = sim.cosine(w.T, k=50, verbose=False, format_output="csr")
+    model_ref = oracle.similarity("cosine", w_ref.T.tocsr(), k=50, format_output="csr")
+    assert_topk_parity(model_ref, model, k=50, rtol=1e-5, what="readme cosine")
+    users = [1, 14, 8, 999]
+    rec = sim.dot_product(urm, model_ref.T, k=100, target_rows=users, filter_cols=urm, verbose=False, format_output="csr")
+    rec_ref = oracle.similarity("dot_product", urm, model_ref.T, k=100, target_rows=users, filter_cols=urm, format_output="csr")
+    assert rec.shape == (1000, 2000)
+    assert_topk_parity(rec_ref, rec, k=100, rtol=1e-5, what="readme recommend")
+    assert set(np.unique(rec.tocoo().row).tolist()) <= set(users)
+    assert rec.multiply(urm).nnz == 0  # seen items are filtered
+
+
+@pytest.mark.parametrize("panel_width", [128, 256, 1024])
+def test_multi_panel_matches_single_panel(panel_width):
+    m = random_csr(500, 1500, 0.02, seed=11)
+    for name, kw in (("cosine", {}), ("jaccard", {}), ("rp3beta", dict(alpha=0.7, beta=0.3))):
+        ref = oracle.similarity(name, m.T.tocsr(), k=30, format_output="csr", **kw)
+        got = getattr(sim, name)(m.T.tocsr(), k=30, verbose=False, format_output="csr",
+                                 tuning=dict(panel_width=panel_width), **kw)
+        assert_topk_parity(ref, got, k=30, rtol=1e-5, what=f"{name} W={panel_width}")
+
+
+@pytest.mark.parametrize("threads,lanes", [(256, 4), (512, 8), (1024, 16), (512, 32)])
+def test_launch_shapes(threads, lanes):
+    m = random_csr(400, 300, 0.05, seed=12, integer=True)
+    ref = oracle.similarity("dot_product", m, k=25, format_output="csr")
+    got = sim.dot_product(m, k=25, verbose=False, format_output="csr", tuning=dict(threads=threads, lanes=lanes))
+    assert_topk_parity(ref, got, k=25, rtol=0.0, what=f"threads={threads} lanes={lanes}")
+
+
+def test_large_k_uses_global_candidate_buffer():
+    m = random_csr(200, 9000, 0.01, seed=13)
+    ref = oracle.similarity("dot_product", m.T.tocsr(), k=5000, format_output="csr")
+    got = sim.dot_product(m.T.tocsr(), k=5000, verbose=False, format_output="csr")
+    assert_topk_parity(ref, got, k=5000, rtol=1e-5, what="k=5000")
+
+
+def test_empty_and_degenerate_inputs():
+    empty = sp.csr_array((50, 40), dtype=np.float32)
+    got = sim.cosine(empty, k=5, verbose=False, format_output="csr")
+    assert got.shape == (50, 50) and got.nnz == 0
+    coo = sim.cosine(empty, k=5, verbose=False, format_output="coo")
+    assert coo.data.shape[0] == 50 * 5 and not coo.data.any()     # the zero-padded slab, like the reference
+    m = random_csr(60, 40, 0.1, seed=14)
+    m = m.tolil(); m[5, :] = 0; m[:, 7] = 0; m = m.tocsr()         # empty row, empty column, explicit zeros dropped
+    m.data[:3] = 0.0
+    ref, got = both("cosine", m, k=7)
+    assert_topk_parity(ref, got, k=7, rtol=1e-5, what="ragged")
+    ref, got = both("dot_product", m, k=1000)                      # k clipped to n_cols (s_plus.pyx:187-188)
+    assert_topk_parity(ref, got, k=60, rtol=1e-5, what="k clipped")
+    got = sim.dot_product(m, k=3, target_rows=[], verbose=False, format_output="csr")
+    assert got.nnz == 0 and got.shape == (60, 60)
+
+
+def test_duplicate_target_rows_and_dtypes():
+    m = random_csr(80, 50, 0.1, seed=15)
+    rows = [4, 4, 9, 4]
+    ref = oracle.similarity("cosine", m, k=6, target_rows=rows, format_output="csr")
+    got = sim.cosine(m, k=6, target_rows=rows, verbose=False, format_output="csr")
+    assert got.nnz == ref.nnz
+    np.testing.assert_allclose(np.sort(got.data), np.sort(ref.data), rtol=1e-5)
+    for dt in (np.float64, np.int32, np.int64):
+        mi = random_csr(80, 50, 0.1, seed=15, integer=True).astype(dt)
+        mi = sp.csr_array((mi.data, mi.indices.astype(np.int64), mi.indptr.astype(np.int64)), shape=mi.shape)
+        ref = oracle.similarity("dot_product", mi, k=6, format_output="csr")
+        got = sim.dot_product(mi, k=6, verbose=False, format_output="csr")
+        assert got.dtype == np.float32
+        assert_topk_parity(ref, got, k=6, rtol=0.0, what=f"dtype {dt}")
+
+
+def test_selectors_against_oracle():
+    m = random_csr(300, 200, 0.05, seed=16)
+    fm = random_csr(300, 300, 0.2, seed=17)
+    tm = random_csr(300, 300, 0.3, seed=18)
+    cases = [dict(filter_cols=[0, 5, 7, 299]), dict(target_cols=np.arange(0, 300, 2)), dict(filter_cols=fm),
+             dict(target_cols=tm), dict(filter_cols=fm, target_cols=tm), dict(filter_cols=[1, 2], target_cols=tm),
+             dict(filter_cols=fm, target_cols=list(range(100))), dict(threshold=0.2), dict(binary=True, filter_cols=[3, 4])]
+    for kw in cases:
+        ref = oracle.similarity("cosine", m.copy(), k=15, format_output="csr", **kw)
+        got = sim.cosine(m.copy(), k=15, verbose=False, format_output="csr", **kw)
+        assert_topk_parity(ref, got, k=15, rtol=1e-5, what=str(list(kw)))
+
+
+def test_input_side_effects_like_reference():
+    """eliminate_zeros() mutates a CSR argument in place (s_plus.pyx:210-211); data is otherwise untouched."""
+    m = random_csr(100, 80, 0.1, seed=19)
+    m.data[::7] = 0.0
+    nnz_before, data_before = m.nnz, m.data.copy()
+    sim.cosine(m, k=5, verbose=False, binary=True)
+    assert m.nnz < nnz_before
+    np.testing.assert_array_equal(m.data, data_before[data_before != 0])
+
+
+def test_device_matrix_chain_matches_host_path():
+    urm = random_csr(900, 400, 0.03, seed=20)
+    host_model = sim.cosine(sim.bm25(urm).T, k=20, verbose=False, format_output="csr")
+    d = sim.to_device(urm)
+    model = sim.cosine(sim.bm25(d).T, k=20, verbose=False, on_device=True)
+    assert isinstance(model, sim.DeviceMatrix) and model.shape == (400, 400)
+    assert_topk_parity(host_model, sim.to_host(model), k=20, rtol=1e-6, what="device chain cosine")
+    rec = sim.dot_product(d, model.T, k=10, filter_cols=urm, target_rows=[0, 5, 899], verbose=False, format_output="csr")
+    rec_ref = oracle.similarity("dot_product", urm, host_model.T, k=10, filter_cols=urm, target_rows=[0, 5, 899], format_output="csr")
+    assert_topk_parity(rec_ref, rec, k=10, rtol=1e-5, what="device chain recommend")
+    for name, kw in (("rp3beta", dict(alpha=0.8, beta=0.5)), ("p3alpha", dict(alpha=1.3))):
+        ref = oracle.similarity(name, urm, k=12, format_output="csr", **kw)
+        got = sim.to_host(getattr(sim, name)(d, k=12, verbose=False, on_device=True, **kw))
+        assert_topk_parity(ref, got, k=12, rtol=1e-5, what=f"device {name}")
+
+
+# ---- size-independent properties at a size the oracle cannot finish in seconds -------------------------
+def test_properties_at_scale():
+    rng = np.random.default_rng(21)
+    m = sp.random_array((20_000, 30_000), density=0.002, format="csr", dtype=np.float32, random_state=rng)
+    k = 40
+    a = sim.cosine(m, k=k, verbose=False, format_output="csr")
+    # (1) symmetry of cosine: s(i,j) == s(j,i) wherever both directions were kept
+    at = a.T.tocsr()
+    both_kept = a.multiply(at > 0)
+    d = abs(both_kept - at.multiply(a > 0))
+    assert d.max() <= 1e-5
+    # (2) self-similarity is 1 and is the row maximum for every non-empty row
+    diag = a.diagonal()
+    nonempty = np.diff(m.indptr) > 0
+    np.testing.assert_allclose(diag[nonempty], 1.0, rtol=1e-5)
+    assert np.all(a.max(axis=1).toarray().ravel()[nonempty] <= 1.0 + 1e-5)
+    # (3) at most k per row, values sorted best-first inside each CSR row (our slab order), all > 0
+    assert np.diff(a.indptr).max() <= k and a.data.min() > 0
+    r = 1234
+    row_vals = a.data[a.indptr[r]:a.indptr[r + 1]]
+    assert np.all(np.diff(row_vals) <= 0)
+    # (4) idempotence of target_rows: a subset call returns exactly those rows
+    sub = [5, 777, 19_999]
+    b = sim.cosine(m, k=k, target_rows=sub, verbose=False, format_output="csr")
+    for r in sub:
+        np.testing.assert_array_equal(b.indices[b.indptr[r]:b.indptr[r + 1]], a.indices[a.indptr[r]:a.indptr[r + 1]])
+        np.testing.assert_array_equal(b.data[b.indptr[r]:b.indptr[r + 1]], a.data[a.indptr[r]:a.indptr[r + 1]])
+    # (5) linearity of dot_product in the values: scaling A by 2 scales every kept value by 2, same columns
+    d1 = sim.dot_product(m, k=k, target_rows=sub, verbose=False, format_output="csr")
+    m2 = m.copy(); m2.data *= 2
+    d2 = sim.dot_product(m2, m.T.tocsr(), k=k, target_rows=sub, verbose=False, format_output="csr")
+    np.testing.assert_array_equal(d1.indices, d2.indices)
+    np.testing.assert_allclose(d2.data, 2 * d1.data, rtol=1e-6)
+    # (6) spot rows against the oracle
+    ref = oracle.similarity("cosine", m, k=k, target_rows=sub, format_output="csr")
+    assert_topk_parity(ref, b, k=k, rtol=1e-5, what="scale spot rows")
