@@ -253,6 +253,8 @@ def run_ours(args):
     log(f"[bench r{rank}] URM {n_users}x{n_items} nnz={nnz} generated+bm25 in {time.perf_counter() - t_setup:.1f}s")
 
     common = dict(k=K_NEIGHBOURS, verbose=False, format_output="csr", device=local)
+    if os.environ.get("SPY_TUNING"):  # kernel experiments only, e.g. SPY_TUNING="threads=512,pairs=0"
+        common["tuning"] = {k: int(v) for k, v in (kv.split("=") for kv in os.environ["SPY_TUNING"].split(","))}
 
     def step_device():
         return sim.cosine(m1, m2, on_device=True, **common)
@@ -286,7 +288,7 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     elapsed_ms = ev0.elapsed_time(ev1)
     kern_ms = float(np.mean([t["start"].elapsed_time(t["end"]) for t in trace]))
-    plan = {k: trace[0][k] for k in ("n_panels", "panel_width", "threads", "lanes")}
+    plan = {k: trace[0][k] for k in ("n_panels", "panel_width", "threads")}
     if world > 1:
         t = torch.tensor([elapsed_ms, kern_ms], device=dev, dtype=torch.float64)
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SPY_ABI_VERSION 1
+#define SPY_ABI_VERSION 2
 
 typedef enum {
     SPY_OK = 0,
@@ -119,14 +119,15 @@ typedef struct spy_knn_args {
     const int32_t *b_split;     /* [b_rows * split_stride] from spy_knn_build_split_dev     */
     int32_t split_stride;
     int32_t n_panels;
-    int32_t threads;            /* 256, 512 or 1024                                         */
-    int32_t lanes_per_segment;  /* 4, 8, 16 or 32                                           */
+    int32_t threads;            /* 512 or 1024 threads per CTA (1024 / threads CTAs per SM)    */
+    const void *b_pairs;        /* B's (column, value) entries packed 8 bytes each by
+                                 * spy_knn_pack_pairs_dev: the layout the kernel streams       */
     const int32_t *row_order;   /* optional permutation of [0,n_targets): processing order  */
 } spy_knn_args;
 
-/* Choose panel_width / n_panels / split_stride / threads / lanes for a problem.
- * avg_b_row_nnz only steers lanes_per_segment.  Fills the plan fields of *args. */
-int spy_knn_plan(spy_knn_args *args, double avg_b_row_nnz, int device);
+/* Choose panel_width / n_panels / split_stride / threads for a problem (device < 0: plan with B200
+ * defaults without touching the CUDA runtime).  Fills the plan fields of *args. */
+int spy_knn_plan(spy_knn_args *args, int device);
 
 /* Bytes of device scratch spy_knn_topk_dev needs for *args (after spy_knn_plan). */
 int64_t spy_knn_scratch_bytes(const spy_knn_args *args, int device);
@@ -137,6 +138,11 @@ int64_t spy_knn_scratch_bytes(const spy_knn_args *args, int device);
 int spy_knn_build_split_dev(int32_t b_rows, const int32_t *b_indptr, const int32_t *b_indices,
                             int32_t panel_width, int32_t n_panels, int32_t split_stride,
                             int32_t *split_out, void *stream);
+
+/* pairs_out[q] = (b_indices[q], bits of b_data[q]) as one 8-byte word per stored entry of B: the layout
+ * the hot kernel streams (one 8-byte gather per product).  pairs_out holds nnz * 8 bytes. */
+int spy_knn_pack_pairs_dev(int64_t nnz, const int32_t *b_indices, const float *b_data, void *pairs_out,
+                           void *stream);
 
 /* The hot path.  Replaces s_plus::compute_similarities_parallel<int,float>
  * (s_plus.h:265-453).  Device pointers; scratch is spy_knn_scratch_bytes() bytes. */

@@ -23,6 +23,7 @@ __global__ void __launch_bounds__(1024) bench(const int* __restrict__ cols, cons
     const float* v = vals + (long)blockIdx.x * n_per_cta;
     float* g = gacc + (long)blockIdx.x * W;
     float s = 0.f;
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(acc);
     const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
     const int Ww = W / nw;  // warp-private width
     float* wacc = acc + warp * Ww;
@@ -43,6 +44,20 @@ __global__ void __launch_bounds__(1024) bench(const int* __restrict__ cols, cons
                 for (int q = 0; q < 4; q++) { if ((lane >> 3) == q) { wacc[cc] += vi[j]; } __syncwarp(); }
             }
             else if (MODE == 6) { int cc = ci[j] % Ww; wacc[cc] += vi[j]; __syncwarp(); }
+            else if (MODE == 7) { unsigned a = sbase + ci[j] * 4; asm volatile("red.shared.add.f32 [%0], %1;" :: "r"(a), "f"(vi[j]) : "memory"); }
+            else if (MODE == 8) {
+                unsigned a = sbase + ci[j] * 4; float old; const float x = vi[j];
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(old) : "r"(a) : "memory");
+                for (;;) { float nv = old + x; unsigned got;
+                    asm volatile("atom.shared.cas.b32 %0, [%1], %2, %3;" : "=r"(got) : "r"(a), "r"(__float_as_uint(old)), "r"(__float_as_uint(nv)) : "memory");
+                    if (got == __float_as_uint(old)) break; old = __uint_as_float(got); }
+            }
+            else if (MODE == 9) {  // two-phase: native int atomic on exponent-aligned fixed point is not general; here: exch-based add
+                unsigned a = sbase + ci[j] * 4; float x = vi[j];
+                // take the slot (swap in a marker), add, put back; retry while marker seen
+                for (;;) { unsigned got; asm volatile("atom.shared.exch.b32 %0, [%1], %2;" : "=r"(got) : "r"(a), "r"(0x7fc00001u) : "memory");
+                    if (got != 0x7fc00001u) { float nv = __uint_as_float(got) + x; asm volatile("st.shared.f32 [%0], %1;" :: "r"(a), "f"(nv) : "memory"); break; } }
+            }
         }
     }
     __syncthreads();
@@ -66,7 +81,7 @@ void run(const char* name, int threads, int ctas_per_sm, int W, const int* cols,
     }
     CK(cudaGetLastError());
     double prods = (double)n_per_cta * grid;
-    printf("%-28s thr=%4d cta/sm=%d W=%6d  %8.3f ms  %7.2f Gprod/s  %6.1f GB/s stream\n", name, threads, ctas_per_sm, W, best, prods / best / 1e6, prods * 8 / best / 1e6);
+    printf("%-34s thr=%4d cta/sm=%d W=%6d  %8.3f ms  %7.2f Gprod/s  %6.1f GB/s stream\n", name, threads, ctas_per_sm, W, best, prods / best / 1e6, prods * 8 / best / 1e6);
     fflush(stdout);
 }
 
@@ -93,6 +108,9 @@ int main() {
         run<4>("global RED.ADD.F32 (L2)", thr, cps, W, cols, vals, N, gacc, out, nsm);
         run<5>("warp-private 8-lane substeps", thr, cps, W, cols, vals, N, gacc, out, nsm);
         run<6>("warp-private full-warp RMW", thr, cps, W, cols, vals, N, gacc, out, nsm);
+        run<7>("red.shared.add.f32 (32-bit addr)", thr, cps, W, cols, vals, N, gacc, out, nsm);
+        run<8>("manual ld + atom.cas loop", thr, cps, W, cols, vals, N, gacc, out, nsm);
+        run<9>("exch-lock add", thr, cps, W, cols, vals, N, gacc, out, nsm);
         if (W == 49152) { run<1>("smem float atomicAdd (CAS)", 512, 1, W, cols, vals, N, gacc, out, nsm); run<1>("smem float atomicAdd (CAS)", 256, 1, W, cols, vals, N, gacc, out, nsm); }
         else { run<1>("smem float atomicAdd (CAS)", 1024, 2, W, cols, vals, N, gacc, out, nsm); run<1>("smem float atomicAdd (CAS)", 256, 2, W, cols, vals, N, gacc, out, nsm);}
     }

@@ -436,10 +436,8 @@ class KnnJob:
         a.filter_mode, a.filter_indptr, a.filter_indices = self.filter_mode, _ptr(self.filter_m[0]), _ptr(self.filter_m[1])
         a.target_mode, a.target_indptr, a.target_indices = self.target_mode, _ptr(self.target_m[0]), _ptr(self.target_m[1])
         a.threads = int(self.tuning.get("threads", 0))
-        a.lanes_per_segment = int(self.tuning.get("lanes", 0))
         a.panel_width = int(self.tuning.get("panel_width", 0))
-        avg = (B.nnz / B.n_rows) if B.n_rows > 0 else 0.0
-        _lib.check(lib.spy_knn_plan(C.byref(a), avg, ctx.index))
+        _lib.check(lib.spy_knn_plan(C.byref(a), ctx.index))
         if a.n_panels > 1:
             if not B.sorted_rows:  # the panel split needs ascending columns inside every row of B
                 _lib.check(lib.spy_csr_sort_rows_dev(B.n_rows, _ptr(B.indptr), _ptr(B.indices), _ptr(B.data), ctx.sptr))
@@ -449,6 +447,11 @@ class KnnJob:
                                                    a.split_stride, _ptr(split), ctx.sptr))
             a.b_split = _ptr(split)
             self.keep.append(split)
+        # 8-byte (column, value) stream layout of B
+        pairs = ctx.empty(max(B.nnz, 1) * 2, torch.int32)
+        _lib.check(lib.spy_knn_pack_pairs_dev(B.nnz, _ptr(B.indices), _ptr(B.data), _ptr(pairs), ctx.sptr))
+        a.b_pairs = _ptr(pairs)
+        self.keep.append(pairs)
         slab = self.n_targets * self.k
         self.out_cols = ctx.empty(slab, torch.int32)
         self.out_vals = ctx.empty(slab, torch.float32)
@@ -473,8 +476,7 @@ class KnnJob:
         if trace is not None:
             ev1.record(self.ctx.stream)
             trace.append(dict(start=ev0, end=ev1, n_targets=self.n_targets, k=self.k, n_panels=int(self.args.n_panels),
-                              panel_width=int(self.args.panel_width), threads=int(self.args.threads),
-                              lanes=int(self.args.lanes_per_segment)))
+                              panel_width=int(self.args.panel_width), threads=int(self.args.threads)))
 
     # ---- output (s_plus.pyx:405-424) --------------------------------------------------------------
     def assemble_device(self, format_output):

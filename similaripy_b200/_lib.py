@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsimilaripy_b200.so")
+# SIMILARIPY_B200_LIB: alternative build of the same library (kernel experiments only)
+LIB_PATH = os.environ.get("SIMILARIPY_B200_LIB") or os.path.join(_HERE, "libsimilaripy_b200.so")
 
 SEL_NONE, SEL_ARRAY, SEL_MATRIX = 0, 1, 2
 F32, F64 = 0, 1
@@ -35,7 +36,7 @@ class KnnArgs(C.Structure):
         ("target_mode", _i32), ("target_indptr", _vp), ("target_indices", _vp),
         ("out_rows", _vp), ("out_cols", _vp), ("out_values", _vp), ("out_counts", _vp),
         ("panel_width", _i32), ("b_split", _vp), ("split_stride", _i32), ("n_panels", _i32),
-        ("threads", _i32), ("lanes_per_segment", _i32), ("row_order", _vp),
+        ("threads", _i32), ("b_pairs", _vp), ("row_order", _vp),
     ]
 
 
@@ -45,7 +46,8 @@ SIGNATURES = {
     "spy_device_count": (C.c_int, []),
     "spy_last_error": (C.c_char_p, []),
     "spy_launch_count": (_i64, [C.c_int]),
-    "spy_knn_plan": (C.c_int, [C.POINTER(KnnArgs), _f64, C.c_int]),
+    "spy_knn_plan": (C.c_int, [C.POINTER(KnnArgs), C.c_int]),
+    "spy_knn_pack_pairs_dev": (C.c_int, [_i64, _vp, _vp, _vp, _vp]),
     "spy_knn_scratch_bytes": (_i64, [C.POINTER(KnnArgs), C.c_int]),
     "spy_knn_build_split_dev": (C.c_int, [_i32, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),
     "spy_knn_topk_dev": (C.c_int, [C.POINTER(KnnArgs), _vp, _i64, _vp]),
@@ -72,6 +74,7 @@ SIGNATURES = {
                                    C.c_int, C.c_int, _f64, _vp, _vp]),
 }
 
+ABI_VERSION = 2
 _lib = None
 
 
@@ -94,7 +97,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError here means header and library disagree
         fn.restype = res
         fn.argtypes = args
-    if lib.spy_abi_version() != 1:
+    if lib.spy_abi_version() != ABI_VERSION:
         raise RuntimeError("similaripy_b200: ABI version mismatch between _lib.py and the shared library")
     _lib = lib
     return lib

@@ -50,13 +50,15 @@ def needs_build() -> bool:
         return f.read().strip() != source_hash()
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, extra_flags=(), out_path: str | None = None) -> str:
+    """Default build: the product library.  extra_flags / out: experimental variants (e.g. -DSPY_UNROLL=4)."""
+    variant = out_path is not None
+    if not variant and not force and not needs_build():
         return LIB
     nvcc = _nvcc()
-    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")] + list(extra_flags)
     objs = []
-    build_dir = os.path.join(HERE, "build")
+    build_dir = os.path.join(HERE, "build" if not variant else "build_" + os.path.basename(out_path))
     os.makedirs(build_dir, exist_ok=True)
     procs = []
     for src in SOURCES:
@@ -75,13 +77,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError(f"nvcc failed on {src}")
     with open(os.path.join(build_dir, "ptxas.log"), "w") as f:
         f.write("\n".join(log))
-    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-lcudart"]
+    target = out_path if variant else LIB
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", target, *objs, "-lcudart"]
     if verbose:
         print(" ".join(cmd))
     subprocess.check_call(cmd)
-    with open(STAMP, "w") as f:
-        f.write(source_hash())
-    return LIB
+    if not variant:
+        with open(STAMP, "w") as f:
+            f.write(source_hash())
+    return target
 
 
 if __name__ == "__main__":

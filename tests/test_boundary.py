@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} is declared in the header but not exported"
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature in _lib.py"
     assert set(_lib.SIGNATURES) == set(declared)
-    assert lib.spy_abi_version() == 1
+    assert lib.spy_abi_version() == _lib.ABI_VERSION == 2
 
 
 def test_struct_layout_matches_c(tmp_path):
@@ -59,10 +59,10 @@ def test_no_compute_needed_entry_points():
     assert lib.spy_tfidf_scratch_bytes(100, 50, _lib.F32) > 0
     a = _lib.KnnArgs()
     a.k, a.n_cols, a.n_targets = 100, 200_000, 1000
-    assert lib.spy_knn_plan(ctypes.byref(a), 50.0, -1) == 0  # device -1: plan with B200 defaults, no CUDA call
+    assert lib.spy_knn_plan(ctypes.byref(a), -1) == 0  # device -1: plan with B200 defaults, no CUDA call
     assert a.n_panels >= 4 and a.panel_width % 128 == 0 and a.panel_width * a.n_panels >= a.n_cols
     a.k = 0
-    assert lib.spy_knn_plan(ctypes.byref(a), 50.0, -1) < 0
+    assert lib.spy_knn_plan(ctypes.byref(a), -1) < 0
     assert b"k must be" in lib.spy_last_error()
 
 
