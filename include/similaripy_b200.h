@@ -153,6 +153,13 @@ int spy_knn_topk_dev(const spy_knn_args *args, void *scratch, int64_t scratch_by
  * host arrays of n_targets*k entries. */
 int spy_knn_topk_host(const spy_knn_args *host_args, int device);
 
+/* work[i] = number of scalar products the expansion of target row i performs,
+ * sum over u in A[targets[i],:] of nnz(B[u,:]).  The reference balances rows over threads with
+ * `omp for schedule(dynamic)` (s_plus.h:337); across GPUs the target rows are cut into contiguous ranges
+ * of equal work instead (similaripy_b200/sharded.py). */
+int spy_knn_row_work_dev(int32_t n_targets, const int32_t *targets, const int32_t *a_indptr,
+                         const int32_t *a_indices, const int32_t *b_indptr, int64_t *work, void *stream);
+
 /* Kernel launches performed by the calling thread since the last call (diagnostics / bench). */
 int64_t spy_launch_count(int reset);
 
@@ -197,7 +204,8 @@ int spy_cast_values_dev(int64_t n, const void *src, int src_dtype, int binary, f
  * eliminate_zeros (utils.pyx:67-173, coo_to_csr.h:28-71, s_plus.pyx:424).
  *   1. spy_slab_row_nnz_dev: row_nnz[targets[i]] = #entries with value != 0 among the first
  *      counts[i] of slab row i (row_nnz has one int per OUTPUT row and must be zeroed first;
- *      target rows must be unique -- duplicates are assembled by the host wrapper);
+ *      target rows must be unique -- duplicates are assembled by the host wrapper; a slab row
+ *      with targets[i] < 0 is padding (gathered slabs of sharded runs) and is skipped);
  *   2. the caller scans row_nnz into csr_indptr (spy_exclusive_scan_i64_dev);
  *   3. spy_slab_compact_dev writes the kept (col, value) pairs at csr_indptr[targets[i]].
  * idx_dtype selects int32 / int64 csr_indices (get_index_dtype, utils.pyx:28-40). */

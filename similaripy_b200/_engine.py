@@ -16,6 +16,7 @@ import numpy as np
 import scipy.sparse as sp
 
 from . import _lib
+from . import sharded as _sharded
 
 # When set to a list, every hot-kernel launch appends {start, end (CUDA events), plan...} to it (bench.py).
 KERNEL_TRACE = None
@@ -341,6 +342,9 @@ class KnnJob:
     out_counts: object = None
     unique_targets: bool = True
     tuning: dict = field(default_factory=dict)
+    shard: object = None      # sharded.ShardPlan when the target rows are split over ranks
+    exchange: object = None   # sharded.SlabExchange when the full result is gathered on every rank
+    targets_np: object = None  # the FULL target list on the host (sharded runs)
 
     # ---- norm vectors (s_plus.pyx:259-269) ------------------------------------------------
     def build_vectors(self, weight_depop_matrix1, weight_depop_matrix2, p1, p2, c1, c2, additive_shrink):
@@ -417,6 +421,61 @@ class KnnJob:
             self.B = filter_csr(ctx, self.B, col_mask=mask, values=raw_b_values)
             self.keep.append(mask)
 
+    # ---- multi-GPU: keep this rank's share of the target rows -----------------------
+    def shard_targets(self, spec, targets_np):
+        """Cut the target list into world contiguous ranges of equal work (scalar products) and keep range
+        `rank`.  Every rank computes the same cut from the same inputs; nothing is communicated."""
+        ctx, torch = self.ctx, self.ctx.torch
+        rank, world = spec.resolve()
+        if self.n_targets > 0:
+            work = ctx.empty(self.n_targets, torch.int64)
+            _lib.check(ctx.lib.spy_knn_row_work_dev(self.n_targets, _ptr(self.targets), _ptr(self.A.indptr),
+                                                    _ptr(self.A.indices), _ptr(self.B.indptr), _ptr(work), ctx.sptr))
+            work_np = work.cpu().numpy()
+        else:
+            work_np = np.zeros(0, dtype=np.int64)
+        self.shard = _sharded.ShardPlan(rank, world, _sharded.balanced_bounds(work_np, world))
+        self.targets_np = targets_np
+        self.targets = self.targets[self.shard.lo: self.shard.hi]
+        self.n_targets = self.shard.n_local
+        if spec.gather:
+            self.exchange = _sharded.SlabExchange(self.shard, self.k, torch, ctx.device)
+            self.gather_group = spec.group
+
+    def gather(self):
+        """All-gather the per-rank slabs in place; afterwards the job describes the FULL result."""
+        ctx, torch = self.ctx, self.ctx.torch
+        plan = self.shard
+        ctx.sync()  # the collective runs on NCCL's stream: the kernel's writes must have landed
+        cols, vals, counts = self.exchange.all_gather(self.gather_group)
+        padded = plan.padded_targets(self.targets_np)
+        if self.unique_targets:  # assemble straight from the padded slab (targets < 0 are skipped)
+            self.out_cols, self.out_vals, self.out_counts = cols, vals, counts
+            self.targets = ctx.h2d(padded)
+            self.n_targets = plan.world * plan.n_max
+            self.padded = True
+        else:  # duplicates take the host assembly path: give it a contiguous slab
+            k, m = self.k, plan.n_max
+            n = [plan.bounds[p + 1] - plan.bounds[p] for p in range(plan.world)]
+            self.out_cols = torch.cat([cols[p * m * k: (p * m + n[p]) * k] for p in range(plan.world)])
+            self.out_vals = torch.cat([vals[p * m * k: (p * m + n[p]) * k] for p in range(plan.world)])
+            self.out_counts = torch.cat([counts[p * m: p * m + n[p]] for p in range(plan.world)])
+            self.targets = ctx.h2d(self.targets_np)
+            self.n_targets = int(self.targets_np.shape[0])
+
+    def compact_padded(self):
+        """Drop the padding rows of a gathered slab (COO keeps every slab entry, s_plus.pyx:351-353)."""
+        if not getattr(self, "padded", False):
+            return
+        plan, k, m, torch = self.shard, self.k, self.shard.n_max, self.ctx.torch
+        n = [plan.bounds[p + 1] - plan.bounds[p] for p in range(plan.world)]
+        self.out_cols = torch.cat([self.out_cols[p * m * k: (p * m + n[p]) * k] for p in range(plan.world)])
+        self.out_vals = torch.cat([self.out_vals[p * m * k: (p * m + n[p]) * k] for p in range(plan.world)])
+        self.out_counts = torch.cat([self.out_counts[p * m: p * m + n[p]] for p in range(plan.world)])
+        self.targets = self.ctx.h2d(self.targets_np)
+        self.n_targets = int(self.targets_np.shape[0])
+        self.padded = False
+
     # ---- plan + split points ------------------------------------------------------------------
     def plan(self):
         ctx, lib, torch = self.ctx, self.ctx.lib, self.ctx.torch
@@ -453,9 +512,12 @@ class KnnJob:
         a.b_pairs = _ptr(pairs)
         self.keep.append(pairs)
         slab = self.n_targets * self.k
-        self.out_cols = ctx.empty(slab, torch.int32)
-        self.out_vals = ctx.empty(slab, torch.float32)
-        self.out_counts = ctx.empty(max(self.n_targets, 1), torch.int32)
+        if self.exchange is not None:  # the kernel writes into this rank's slice of the all-gather buffer
+            self.out_cols, self.out_vals, self.out_counts = self.exchange.local()
+        else:
+            self.out_cols = ctx.empty(slab, torch.int32)
+            self.out_vals = ctx.empty(slab, torch.float32)
+            self.out_counts = ctx.empty(max(self.n_targets, 1), torch.int32)
         a.out_rows = None
         a.out_cols, a.out_values, a.out_counts = _ptr(self.out_cols), _ptr(self.out_vals), _ptr(self.out_counts)
         sb = int(lib.spy_knn_scratch_bytes(C.byref(a), ctx.index))
@@ -484,6 +546,8 @@ class KnnJob:
         ctx, lib, torch = self.ctx, self.ctx.lib, self.ctx.torch
         k, nt = self.k, self.n_targets
         if format_output == "coo":
+            self.compact_padded()
+            nt = self.n_targets
             rows = ctx.empty(nt * k, torch.int32)
             _lib.check(lib.spy_slab_fill_rows_dev(nt, k, _ptr(self.targets), _ptr(self.out_counts), _ptr(rows), ctx.sptr))
             return ("coo", rows, self.out_cols, self.out_vals)
@@ -495,7 +559,8 @@ class KnnJob:
         indptr = ctx.scan_i64(row_nnz)
         nnz = int(indptr[-1].item())
         # get_index_dtype(max(len(values), n_cols)) on the PADDED slab length, utils.pyx:165-168
-        idx64 = max(nt * k, self.n_cols) > INT32_MAX
+        n_full = nt if self.targets_np is None or self.exchange is None else int(self.targets_np.shape[0])
+        idx64 = max(n_full * k, self.n_cols) > INT32_MAX
         indices = ctx.empty(nnz, torch.int64 if idx64 else torch.int32)
         data = ctx.empty(nnz, torch.float32)
         _lib.check(lib.spy_slab_compact_dev(nt, k, _ptr(self.out_cols), _ptr(self.out_vals), _ptr(self.out_counts),
@@ -582,6 +647,9 @@ def prepare_job(matrix1, matrix2=None, weight_depop_matrix1="none", weight_depop
                  n_rows=n_rows, n_cols=n_cols, params=params, unique_targets=unique, tuning=dict(tuning or {}))
     job.build_vectors(weight_depop_matrix1, weight_depop_matrix2, f32(p1), f32(p2), f32(c1), f32(c2), f32(additive_shrink))
     job.build_selectors(filter_cols, target_cols, raw_b)
+    spec = _sharded.active()
+    if spec is not None:
+        job.shard_targets(spec, targets_np)
     job.plan()
     return job
 
@@ -604,6 +672,8 @@ def s_plus(matrix1, matrix2=None, weight_depop_matrix1="none", weight_depop_matr
                       device, tuning)
     if job.n_targets > 0:
         job.run()
+    if job.exchange is not None:
+        job.gather()
     if on_device:
         return job.to_device_matrix()
     return job.to_host(job.assemble_device(format_output))

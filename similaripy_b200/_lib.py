@@ -50,6 +50,7 @@ SIGNATURES = {
     "spy_knn_pack_pairs_dev": (C.c_int, [_i64, _vp, _vp, _vp, _vp]),
     "spy_knn_scratch_bytes": (_i64, [C.POINTER(KnnArgs), C.c_int]),
     "spy_knn_build_split_dev": (C.c_int, [_i32, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),
+    "spy_knn_row_work_dev": (C.c_int, [_i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "spy_knn_topk_dev": (C.c_int, [C.POINTER(KnnArgs), _vp, _i64, _vp]),
     "spy_knn_topk_host": (C.c_int, [C.POINTER(KnnArgs), C.c_int]),
     "spy_csr_row_sum_dev": (C.c_int, [_i32, _vp, _vp, C.c_int, _vp, _vp]),

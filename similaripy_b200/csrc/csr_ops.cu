@@ -54,6 +54,29 @@ __global__ void row_sum_kernel(int n_rows, const int *__restrict__ indptr, const
     }
 }
 
+// ---- work per target row: number of scalar products its expansion performs --------------
+// w(t) = sum over u in A[t,:] of nnz(B[u,:]); the unit the row partition across GPUs is balanced by.
+__global__ void row_work_kernel(int n_targets, const int *__restrict__ targets, const int *__restrict__ a_indptr,
+                                const int *__restrict__ a_indices, const int *__restrict__ b_indptr,
+                                long long *__restrict__ work) {
+    const int lane = threadIdx.x & 31;
+    const int warp0 = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const int nwarps = gridDim.x * kWarpsPerBlock;
+    for (int i = warp0; i < n_targets; i += nwarps) {
+        const int t = targets[i];
+        const int s = a_indptr[t], e = a_indptr[t + 1];
+        int acc = 0;  // a row's products fit int32 whenever nnz(B) does
+        for (int q = s + lane; q < e; q += 32) {
+            const int u = a_indices[q];
+            acc += b_indptr[u + 1] - b_indptr[u];
+        }
+        long long w = acc;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+        if (lane == 0) work[i] = w;
+    }
+}
+
 // ---- column sums (fp64 accumulation like np.bincount(weights=...)) -----------------------
 template <bool SQUARE>
 __global__ void col_sum_kernel(long long nnz, const int *__restrict__ indices, const float *__restrict__ data,
@@ -359,6 +382,7 @@ __global__ void slab_row_nnz_kernel(int n_targets, int k, const float *__restric
     const int warp0 = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     const int nwarps = gridDim.x * kWarpsPerBlock;
     for (int i = warp0; i < n_targets; i += nwarps) {
+        if (targets[i] < 0) continue;  // padding row of a gathered slab (sharded runs)
         const int n = counts[i];
         const float *v = values + (size_t)i * k;
         int c = 0;
@@ -376,6 +400,7 @@ __global__ void slab_compact_kernel(int n_targets, int k, const int *__restrict_
     const int warp0 = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     const int nwarps = gridDim.x * kWarpsPerBlock;
     for (int i = warp0; i < n_targets; i += nwarps) {
+        if (targets[i] < 0) continue;  // padding row of a gathered slab (sharded runs)
         const int n = counts[i];
         const size_t o = (size_t)i * k;
         long long dst = csr_indptr[targets[i]];
@@ -398,7 +423,7 @@ __global__ void slab_fill_rows_kernel(int n_targets, int k, const int *__restric
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += stride) {
         const int i = (int)(q / k), j = (int)(q % k);
-        rows[q] = (j < counts[i]) ? targets[i] : 0;
+        rows[q] = (targets[i] >= 0 && j < counts[i]) ? targets[i] : 0;
     }
 }
 
@@ -413,6 +438,16 @@ int spy_csr_row_sum_dev(int32_t n_rows, const int32_t *indptr, const float *data
     const int grid = grid_for(n_rows, kWarpsPerBlock);
     if (square) row_sum_kernel<true><<<grid, kThreads, 0, as_stream(stream)>>>(n_rows, indptr, data, out);
     else row_sum_kernel<false><<<grid, kThreads, 0, as_stream(stream)>>>(n_rows, indptr, data, out);
+    SPY_LAUNCH_OK();
+    return SPY_OK;
+}
+
+int spy_knn_row_work_dev(int32_t n_targets, const int32_t *targets, const int32_t *a_indptr, const int32_t *a_indices,
+                         const int32_t *b_indptr, int64_t *work, void *stream) {
+    if (n_targets <= 0) return SPY_OK;
+    SPY_REQUIRE(targets && a_indptr && b_indptr && work, "row_work: NULL pointer");
+    row_work_kernel<<<grid_for(n_targets, kWarpsPerBlock), kThreads, 0, as_stream(stream)>>>(
+        n_targets, targets, a_indptr, a_indices, b_indptr, reinterpret_cast<long long *>(work));
     SPY_LAUNCH_OK();
     return SPY_OK;
 }
