@@ -288,7 +288,7 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     elapsed_ms = ev0.elapsed_time(ev1)
     kern_ms = float(np.mean([t["start"].elapsed_time(t["end"]) for t in trace]))
-    plan = {k: trace[0][k] for k in ("n_panels", "panel_width", "threads")}
+    plan = {k: trace[0][k] for k in ("n_panels", "panel_width", "threads", "group")}
     if world > 1:
         t = torch.tensor([elapsed_ms, kern_ms], device=dev, dtype=torch.float64)
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
@@ -312,7 +312,7 @@ def run_ours(args):
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": None,
                 "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)" if peaks else "fallback 6650",
-                "kernel": "knn_panel_kernel", "kernel_ms": round(kern_ms, 3), "algorithmic_bytes": alg_bytes,
+                "kernel": "knn_flat_kernel", "kernel_ms": round(kern_ms, 3), "algorithmic_bytes": alg_bytes,
                 "products": products, "gproducts_per_s": round(products / (kern_ms / 1e3) / 1e9, 1),
                 "kernel_share_of_step": round(kern_ms / ms_per_step, 4), "plan": plan}
     traffic_file = os.path.join(ROOT, "profiles", "knn_traffic.json")

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SPY_ABI_VERSION 2
+#define SPY_ABI_VERSION 3
 
 typedef enum {
     SPY_OK = 0,
@@ -123,9 +123,12 @@ typedef struct spy_knn_args {
     const void *b_pairs;        /* B's (column, value) entries packed 8 bytes each by
                                  * spy_knn_pack_pairs_dev: the layout the kernel streams       */
     const int32_t *row_order;   /* optional permutation of [0,n_targets): processing order  */
+    int64_t b_nnz;              /* stored entries of B (b_indptr[b_rows]); 0 = unknown: only used to
+                                 * size `group` from the mean segment length                      */
+    int32_t group;              /* lanes streaming one B-row segment together: 4, 8, 16 or 32      */
 } spy_knn_args;
 
-/* Choose panel_width / n_panels / split_stride / threads for a problem (device < 0: plan with B200
+/* Choose panel_width / n_panels / split_stride / threads / group for a problem (device < 0: plan with B200
  * defaults without touching the CUDA runtime).  Fills the plan fields of *args. */
 int spy_knn_plan(spy_knn_args *args, int device);
 
@@ -140,7 +143,8 @@ int spy_knn_build_split_dev(int32_t b_rows, const int32_t *b_indptr, const int32
                             int32_t *split_out, void *stream);
 
 /* pairs_out[q] = (b_indices[q], bits of b_data[q]) as one 8-byte word per stored entry of B: the layout
- * the hot kernel streams (one 8-byte gather per product).  pairs_out holds nnz * 8 bytes. */
+ * the hot kernel streams (16-byte gathers of two pairs).  pairs_out holds (nnz + 1) * 8 bytes, 16-byte aligned
+ * (the kernel may read one pair past the end; its content is ignored). */
 int spy_knn_pack_pairs_dev(int64_t nnz, const int32_t *b_indices, const float *b_data, void *pairs_out,
                            void *stream);
 

@@ -496,6 +496,8 @@ class KnnJob:
         a.target_mode, a.target_indptr, a.target_indices = self.target_mode, _ptr(self.target_m[0]), _ptr(self.target_m[1])
         a.threads = int(self.tuning.get("threads", 0))
         a.panel_width = int(self.tuning.get("panel_width", 0))
+        a.group = int(self.tuning.get("group", 0))
+        a.b_nnz = B.nnz
         _lib.check(lib.spy_knn_plan(C.byref(a), ctx.index))
         if a.n_panels > 1:
             if not B.sorted_rows:  # the panel split needs ascending columns inside every row of B
@@ -507,7 +509,7 @@ class KnnJob:
             a.b_split = _ptr(split)
             self.keep.append(split)
         # 8-byte (column, value) stream layout of B
-        pairs = ctx.empty(max(B.nnz, 1) * 2, torch.int32)
+        pairs = ctx.empty((max(B.nnz, 1) + 1) * 2, torch.int32)  # +1: the kernel reads 16-byte words
         _lib.check(lib.spy_knn_pack_pairs_dev(B.nnz, _ptr(B.indices), _ptr(B.data), _ptr(pairs), ctx.sptr))
         a.b_pairs = _ptr(pairs)
         self.keep.append(pairs)
@@ -538,7 +540,8 @@ class KnnJob:
         if trace is not None:
             ev1.record(self.ctx.stream)
             trace.append(dict(start=ev0, end=ev1, n_targets=self.n_targets, k=self.k, n_panels=int(self.args.n_panels),
-                              panel_width=int(self.args.panel_width), threads=int(self.args.threads)))
+                              panel_width=int(self.args.panel_width), threads=int(self.args.threads),
+                              group=int(self.args.group)))
 
     # ---- output (s_plus.pyx:405-424) --------------------------------------------------------------
     def assemble_device(self, format_output):

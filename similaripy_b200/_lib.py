@@ -37,6 +37,7 @@ class KnnArgs(C.Structure):
         ("out_rows", _vp), ("out_cols", _vp), ("out_values", _vp), ("out_counts", _vp),
         ("panel_width", _i32), ("b_split", _vp), ("split_stride", _i32), ("n_panels", _i32),
         ("threads", _i32), ("b_pairs", _vp), ("row_order", _vp),
+        ("b_nnz", _i64), ("group", _i32),
     ]
 
 
@@ -75,7 +76,7 @@ SIGNATURES = {
                                    C.c_int, C.c_int, _f64, _vp, _vp]),
 }
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 _lib = None
 
 
