@@ -17,7 +17,7 @@ __global__ void __launch_bounds__(1024) bench(const int* __restrict__ cols, cons
     extern __shared__ float acc[];
     int* iacc = (int*)acc;
     const int tid = threadIdx.x, nt = blockDim.x;
-    if (MODE != 4) { for (int i = tid; i < W; i += nt) acc[i] = 0.f; }
+    if (MODE != 4) { for (int i = tid; i < W; i += nt) acc[i] = (MODE >= 10 && MODE != 12) ? -0.0f : 0.f; }
     __syncthreads();
     const int* c = cols + (long)blockIdx.x * n_per_cta;
     const float* v = vals + (long)blockIdx.x * n_per_cta;
@@ -57,6 +57,33 @@ __global__ void __launch_bounds__(1024) bench(const int* __restrict__ cols, cons
                 // take the slot (swap in a marker), add, put back; retry while marker seen
                 for (;;) { unsigned got; asm volatile("atom.shared.exch.b32 %0, [%1], %2;" : "=r"(got) : "r"(a), "r"(0x7fc00001u) : "memory");
                     if (got != 0x7fc00001u) { float nv = __uint_as_float(got) + x; asm volatile("st.shared.f32 [%0], %1;" :: "r"(a), "f"(nv) : "memory"); break; } }
+            }
+            else if (MODE == 10 || MODE == 13) {  // swap-carry add: take the slot's value out, add, put back; re-add whatever came back
+                int cc = (MODE == 13) ? ((ci[j] & ~31) | lane) : ci[j];
+                unsigned a = sbase + cc * 4; float carry = vi[j];
+                do { unsigned got;
+                    asm volatile("atom.shared.exch.b32 %0, [%1], %2;" : "=r"(got) : "r"(a), "r"(0x80000000u) : "memory");
+                    carry += __uint_as_float(got);
+                    asm volatile("atom.shared.exch.b32 %0, [%1], %2;" : "=r"(got) : "r"(a), "r"(__float_as_uint(carry)) : "memory");
+                    carry = __uint_as_float(got);
+                } while (__float_as_uint(carry) != 0x80000000u);
+            }
+            else if (MODE == 12) { unsigned a = sbase + ((ci[j] & ~31) | lane) * 4; asm volatile("red.shared.add.f32 [%0], %1;" :: "r"(a), "f"(vi[j]) : "memory"); }
+        }
+        if (MODE == 11) {  // swap-carry, the 4 adds of the step interleaved
+            unsigned a[4], got[4]; float carry[4];
+            #pragma unroll
+            for (int j = 0; j < 4; j++) { a[j] = sbase + ci[j] * 4; asm volatile("atom.shared.exch.b32 %0, [%1], %2;" : "=r"(got[j]) : "r"(a[j]), "r"(0x80000000u)); }
+            #pragma unroll
+            for (int j = 0; j < 4; j++) { carry[j] = vi[j] + __uint_as_float(got[j]); asm volatile("atom.shared.exch.b32 %0, [%1], %2;" : "=r"(got[j]) : "r"(a[j]), "r"(__float_as_uint(carry[j]))); }
+            #pragma unroll
+            for (int j = 0; j < 4; j++) {
+                float c2 = __uint_as_float(got[j]);
+                while (__float_as_uint(c2) != 0x80000000u) { unsigned g2;
+                    asm volatile("atom.shared.exch.b32 %0, [%1], %2;" : "=r"(g2) : "r"(a[j]), "r"(0x80000000u) : "memory");
+                    c2 += __uint_as_float(g2);
+                    asm volatile("atom.shared.exch.b32 %0, [%1], %2;" : "=r"(g2) : "r"(a[j]), "r"(__float_as_uint(c2)) : "memory");
+                    c2 = __uint_as_float(g2); }
             }
         }
     }
@@ -111,6 +138,10 @@ int main() {
         run<7>("red.shared.add.f32 (32-bit addr)", thr, cps, W, cols, vals, N, gacc, out, nsm);
         run<8>("manual ld + atom.cas loop", thr, cps, W, cols, vals, N, gacc, out, nsm);
         run<9>("exch-lock add", thr, cps, W, cols, vals, N, gacc, out, nsm);
+        run<10>("swap-carry add (2 exch)", thr, cps, W, cols, vals, N, gacc, out, nsm);
+        run<11>("swap-carry add, 4 interleaved", thr, cps, W, cols, vals, N, gacc, out, nsm);
+        run<12>("red.shared.add.f32, distinct banks", thr, cps, W, cols, vals, N, gacc, out, nsm);
+        run<13>("swap-carry add, distinct banks", thr, cps, W, cols, vals, N, gacc, out, nsm);
         if (W == 49152) { run<1>("smem float atomicAdd (CAS)", 512, 1, W, cols, vals, N, gacc, out, nsm); run<1>("smem float atomicAdd (CAS)", 256, 1, W, cols, vals, N, gacc, out, nsm); }
         else { run<1>("smem float atomicAdd (CAS)", 1024, 2, W, cols, vals, N, gacc, out, nsm); run<1>("smem float atomicAdd (CAS)", 256, 2, W, cols, vals, N, gacc, out, nsm);}
     }

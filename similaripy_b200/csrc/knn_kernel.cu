@@ -73,11 +73,11 @@ static int make_plan(const spy_knn_args &a, int device, Plan &pl) {
         set_error("threads must be 512 or 1024 (got %d)", pl.threads);
         return SPY_ERR_INVALID;
     }
-    pl.ctas_per_sm = 1;  // 512 threads: 128 registers per thread (deeper gathers in flight), 1024: 64
+    pl.ctas_per_sm = 1024 / pl.threads;  // 64 registers per thread either way
     pl.cap = std::max(2048, next_pow2(2 * std::max(a.k, 1)));
     pl.cand_smem = (size_t)pl.cap * 8 <= 65536;
     // staged target-row chunk: 8 bytes per thread (doubles as the selection's scratch)
-    const size_t fixed = (size_t)pl.threads * 8 + (pl.cand_smem ? (size_t)pl.cap * 8 : 0);
+    const size_t fixed = (size_t)stage_entries(pl.threads) * 8 + (pl.cand_smem ? (size_t)pl.cap * 8 : 0);
     // 1 KB per CTA is reserved by the driver; keep a little slack for static shared memory
     const size_t budget = (size_t)di.max_smem_optin / pl.ctas_per_sm - 1024 - 256;
     if (budget <= fixed + 128 * 4) {
@@ -250,6 +250,7 @@ int spy_knn_topk_dev(const spy_knn_args *args, void *scratch, int64_t scratch_by
     d.target_mode = a.target_mode; d.t_indptr = a.target_indptr; d.t_indices = a.target_indices;
     d.out_rows = a.out_rows; d.out_cols = a.out_cols; d.out_vals = a.out_values; d.out_counts = a.out_counts;
     d.work_counter = reinterpret_cast<int *>(scratch);
+    d.phase = reinterpret_cast<u64 *>(reinterpret_cast<unsigned char *>(scratch) + 128);
     d.cand_global = reinterpret_cast<u64 *>(reinterpret_cast<unsigned char *>(scratch) + 256);
 
     cudaStream_t st = as_stream(stream);

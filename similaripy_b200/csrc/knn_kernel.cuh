@@ -58,6 +58,7 @@ struct KnnDev {
     float *out_vals;
     int *out_counts;
     int *work_counter;
+    u64 *phase;  // SPY_PHASE_TIMING builds: 8 cycle counters summed over CTAs (in the scratch header)
     u64 *cand_global;
 };
 
@@ -158,17 +159,56 @@ __device__ void sort_and_publish(u64 *buf, int n, int k, u64 *cand, int *s_cnt, 
     __syncthreads();
 }
 
+// Rank sort: every live key of buf[0, n) counts the keys that beat it and lands at cand[rank] when rank < k
+// (keys are distinct: they carry the column).  n^2 / NT comparisons per thread and four barriers, against
+// 36-55 barrier-separated compare-exchange steps of the bitonic network: the cheaper one below ~600 keys.
+// buf must not alias cand.  NT / P threads share one key (P = n rounded up to a power of two >= 32).
 template <int NT>
-__device__ void select_topk(u64 *cand, int n, int k, u64 *tmp, int tmp_cap, int *s_cnt, u64 *s_tau, int *s_live,
-                            u64 *s_pivot) {
+__device__ void rank_and_publish(const u64 *buf, int n, int k, u64 *cand, int *s_cnt, u64 *s_tau, int *s_live) {
     const int tid = threadIdx.x;
-    // pivot rank among 64 sorted samples: mean + 3 sigma above the sample quantile of the k-th best
-    const float q = 65.f * (float)k / (float)max(n, 1);
-    const int j = (int)ceilf(q + 3.f * sqrtf(q) + 1.5f);
-    if (n <= 512 || j > 40 || 2 * k > tmp_cap) {  // small buffer or k too close to n: sort it all
-        sort_and_publish<NT>(cand, n, k, cand, s_cnt, s_tau, s_live);
-        return;
+    int P = 32;
+    while (P < n) P <<= 1;
+    if (tid == 0) *s_live = 0;
+    __syncthreads();
+    int live = 0;
+    if (P <= NT) {
+        const int tpk = NT / P;  // power of two <= 32: the threads of a key are neighbouring lanes
+        const int i = tid / tpk, part = tid & (tpk - 1);
+        const u64 key = (i < n) ? buf[i] : 0ull;
+        int cnt = 0;
+        for (int j = part; j < n; j += tpk) cnt += (buf[j] > key) ? 1 : 0;
+        for (int o = tpk >> 1; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        if (part == 0 && key != 0ull) {
+            live = 1;
+            if (cnt < k) cand[cnt] = key;
+        }
+    } else {
+        for (int i = tid; i < n; i += NT) {
+            const u64 key = buf[i];
+            if (key == 0ull) continue;
+            int cnt = 0;
+            for (int j = 0; j < n; j++) cnt += (buf[j] > key) ? 1 : 0;
+            live++;
+            if (cnt < k) cand[cnt] = key;
+        }
     }
+    for (int o = 16; o > 0; o >>= 1) live += __shfl_xor_sync(0xffffffffu, live, o);
+    if ((tid & 31) == 0 && live) atomicAdd(s_live, live);
+    __syncthreads();
+    const int m = min(*s_live, k);
+    if (tid == 0) {
+        *s_cnt = m;
+        if (m == k) *s_tau = cand[k - 1];
+    }
+    __syncthreads();
+}
+
+// One sampling round of the selection: one warp sorts 64 strided samples of cand[0, n), a pivot is picked a safe
+// distance (3 sigma) below the sample quantile of the k-th best, and the keys above the pivot are compacted
+// into tmp.  Returns their number c (block-uniform); the caller checks k <= c <= tmp_cap.
+template <int NT>
+__device__ int pivot_compact(const u64 *cand, int n, int j, u64 *tmp, int tmp_cap, int *s_live, u64 *s_pivot) {
+    const int tid = threadIdx.x;
     if (tid < 64) tmp[tid] = cand[(int)(((long long)tid * n) >> 6)];
     if (tid == 0) *s_live = 0;
     __syncthreads();
@@ -196,11 +236,66 @@ __device__ void select_topk(u64 *cand, int n, int k, u64 *tmp, int tmp_cap, int 
     __syncthreads();
     const int c = *s_live;
     __syncthreads();
-    if (c < k || c > tmp_cap) {  // unlucky pivot: exact fallback
-        sort_and_publish<NT>(cand, n, k, cand, s_cnt, s_tau, s_live);
+    return c;
+}
+// pivot rank among 64 sorted samples for "the k-th best of n": its expected rank q plus 3 sigma
+__device__ __forceinline__ int pivot_rank(int n, int k) {
+    const float q = 65.f * (float)k / (float)max(n, 1);
+    return (int)ceilf(q + 3.f * sqrtf(q) + 1.5f);
+}
+
+// Exact selection: leaves the best m = min(k, #live) keys sorted best-first in cand[0, m), *s_cnt = m and,
+// when m == k, *s_tau = the k-th.  Sampling rounds shrink the buffer to a few hundred keys, a rank sort
+// orders them; an unlucky pivot (fewer than k keys above it, or tmp overflow) falls back to the full bitonic
+// sort -- results never depend on the sampling.
+template <int NT>
+__device__ void select_topk(u64 *cand, int n, int k, u64 *tmp, int tmp_cap, int *s_cnt, u64 *s_tau, int *s_live,
+                            u64 *s_pivot) {
+    const int tid = threadIdx.x;
+    for (int round = 0; round < 3; round++) {
+        const int j = pivot_rank(n, k);
+        if (n <= 2 * k || n <= 192 || j > 40) break;
+        const int c = pivot_compact<NT>(cand, n, j, tmp, tmp_cap, s_live, s_pivot);
+        if (c < k || c > tmp_cap) break;  // unlucky pivot: keep what we have
+        for (int i = tid; i < c; i += NT) cand[i] = tmp[i];
+        n = c;
+        __syncthreads();
+    }
+    if (n <= tmp_cap && n <= 640) {
+        for (int i = tid; i < n; i += NT) tmp[i] = cand[i];
+        __syncthreads();
+        rank_and_publish<NT>(tmp, n, k, cand, s_cnt, s_tau, s_live);
         return;
     }
-    sort_and_publish<NT>(tmp, c, k, cand, s_cnt, s_tau, s_live);
+    sort_and_publish<NT>(cand, n, k, cand, s_cnt, s_tau, s_live);
+}
+
+// Cheap selection between panels: sampling rounds only.  Leaves c >= k unsorted survivors in cand[0, c) with
+// *s_cnt = c and *s_tau = the last pivot -- a valid lower bound of the k-th best, because at least k keys beat
+// it -- or falls back to the exact selection when the first pivot fails.
+template <int NT>
+__device__ void tighten_topk(u64 *cand, int n, int k, u64 *tmp, int tmp_cap, int *s_cnt, u64 *s_tau, int *s_live,
+                             u64 *s_pivot) {
+    const int tid = threadIdx.x;
+    bool done_one = false;
+    u64 tau = 0ull;
+    for (int round = 0; round < 3; round++) {
+        const int j = pivot_rank(n, k);
+        if (n <= 2 * k || j > 40) break;
+        const int c = pivot_compact<NT>(cand, n, j, tmp, tmp_cap, s_live, s_pivot);
+        if (c < k || c > tmp_cap) break;
+        tau = *s_pivot;
+        for (int i = tid; i < c; i += NT) cand[i] = tmp[i];
+        n = c;
+        done_one = true;
+        __syncthreads();
+    }
+    if (!done_one) {
+        select_topk<NT>(cand, n, k, tmp, tmp_cap, s_cnt, s_tau, s_live, s_pivot);
+        return;
+    }
+    if (tid == 0) { *s_cnt = n; *s_tau = tau; }
+    __syncthreads();
 }
 
 // ---- fast pre-filter of the drain ---------------------------------------------------------------
@@ -275,15 +370,16 @@ __device__ __forceinline__ void smem_add_f32(unsigned addr, float x) {
     asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(addr), "f"(x) : "memory");
 }
 
-// 16-byte gathers (two pairs each) a lane has in flight before its first add: 64 registers per thread at
-// 1024 threads per CTA leave room for 4, 128 registers at 512 threads for 8
+// 16-byte gathers (two pairs each) a lane has in flight before its first add; 64 registers per thread
+// (1024 resident threads per SM: one CTA of 1024 or two of 512) leave room for 4
 #ifndef SPY_UNROLL
 #define SPY_UNROLL 4
 #endif
-#ifndef SPY_UNROLL_512
-#define SPY_UNROLL_512 8
-#endif
-__host__ __device__ constexpr int unroll_for(int threads) { return threads == 512 ? SPY_UNROLL_512 : SPY_UNROLL; }
+__host__ __device__ constexpr int unroll_for(int threads) { return SPY_UNROLL; }
+// Entries of a target row staged in shared memory at a time (8 bytes each): a quarter more than the CTA has
+// threads, so that rows a little longer than the thread count (e.g. ~1000 +- 32 entries against 1024 threads)
+// do not pay a second, nearly empty chunk in every panel.
+__host__ __device__ constexpr int stage_entries(int threads) { return threads + threads / 4; }
 
 // shared-memory vector accesses on 32-bit shared addresses (the generic-pointer forms make ptxas rebuild
 // the shared window base inside the loops)
@@ -314,82 +410,147 @@ __device__ __forceinline__ bool push_raw(u64 *cand, int *s_cnt, int cap, float x
 // after the caller has evaluated + selected (which raises tau), so no slot is scanned twice.
 // An untouched slot holds -0.0f: with lo > 0 it fails "x >= lo * den" like any small dot product, so the
 // common path needs no separate "touched" test -- only survivors are checked against the sentinel.
+// "this slot cannot enter the result": x < lo * den for den safely positive (see above)
+template <int KIND>
+__device__ __forceinline__ bool slot_rejected(const KnnDev &p, const FastRow &fr, float x, float lo, float yt, float yc,
+                                              float yd) {
+    if (KIND == KIND_RAW) return x < lo;
+    if (KIND == KIND_C) {
+        const float den = fmaf(fr.cC, yc, fr.A0);
+        return den > 0.f && x < lo * den;
+    }
+    float den = fr.A0, sab = fabsf(fr.A0);
+    if (KIND == KIND_T || (KIND == KIND_GEN && p.l1 != 0.f)) {
+        const float u = fr.cT * yt, w = fr.cX * x;
+        den += u + w;
+        sab += fabsf(u) + fabsf(w);
+    }
+    if (KIND == KIND_GEN && p.l2 != 0.f) {
+        const float u = fr.cC * yc;
+        den += u;
+        sab += fabsf(u);
+    }
+    if (KIND == KIND_D || (KIND == KIND_GEN && p.l3 != 0.f)) {
+        const float u = fr.cD * yd;
+        den += u;
+        sab += fabsf(u);
+    }
+    // den huge / inf: lo * den is +-inf or NaN and the comparison does the right thing
+    return den > 0.f && x < lo * den && den * 64.f >= sab;
+}
+
+// the four slots of a quad at once; KIND_C and KIND_RAW fold the bound into one FFMA + compare per slot:
+// x < lo * (cC * y + A0)  ==  x < (lo * cC) * y + lo * A0  (den >= 0 for these kinds: norms and shrink are
+// non-negative; the regrouping moves the bound by a few ulp, far inside its 1e-4 safety margin)
+template <int KIND>
+__device__ __forceinline__ bool quad_rejected(const KnnDev &p, const FastRow &fr, float lo, float lc, float la,
+                                              const float4 &x, const float4 &yt, const float4 &yc, const float4 &yd) {
+    if (KIND == KIND_RAW) return (x.x < lo) & (x.y < lo) & (x.z < lo) & (x.w < lo);
+    if (KIND == KIND_C)
+        return (x.x < fmaf(lc, yc.x, la)) & (x.y < fmaf(lc, yc.y, la)) & (x.z < fmaf(lc, yc.z, la)) & (x.w < fmaf(lc, yc.w, la));
+    return slot_rejected<KIND>(p, fr, x.x, lo, yt.x, yc.x, yd.x) & slot_rejected<KIND>(p, fr, x.y, lo, yt.y, yc.y, yd.y) &
+           slot_rejected<KIND>(p, fr, x.z, lo, yt.z, yc.z, yd.z) & slot_rejected<KIND>(p, fr, x.w, lo, yt.w, yc.w, yd.w);
+}
+
+constexpr int kDrainDone = 0x3fffffff;  // resume index of a thread that has also finished the partial last quad
+#ifndef SPY_DRAIN_UNROLL
+#define SPY_DRAIN_UNROLL 1
+#endif
+constexpr int kDrainUnroll = SPY_DRAIN_UNROLL;  // quads a thread has in flight: their Y vectors come from L2 (227 KB of
+                                                // shared memory leave no L1)
+
+// Survivors of one quad: touched slots that pass the per-slot filter are buffered; a slot that does not fit keeps its
+// value.  Returns false when the buffer was full.
+template <int KIND>
+__device__ __forceinline__ bool drain_quad_slow(const KnnDev &p, const FastRow &fr, bool filter, float lo, unsigned a, int col0,
+                                                const float4 &x, const float4 &yt, const float4 &yc, const float4 &yd,
+                                                u64 *cand, int *s_cnt) {
+    const float sent = __uint_as_float(kSentinelBits);
+    const float xs[4] = {x.x, x.y, x.z, x.w};
+    const float yts[4] = {yt.x, yt.y, yt.z, yt.w}, ycs[4] = {yc.x, yc.y, yc.z, yc.w}, yds[4] = {yd.x, yd.y, yd.z, yd.w};
+    unsigned m = 0u;  // the quad's survivors
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+        if (__float_as_uint(xs[r]) != kSentinelBits && !(filter && slot_rejected<KIND>(p, fr, xs[r], lo, yts[r], ycs[r], yds[r])))
+            m |= 1u << r;
+    if (m == 0u) {
+        sts128(a, make_float4(sent, sent, sent, sent));
+        return true;
+    }
+    // one reservation for all of them (a thread-level atomic: the few lanes with survivors serialise on s_cnt)
+    const int cnt = __popc(m);
+    int pos = p.cap;
+    if (*reinterpret_cast<volatile int *>(s_cnt) < p.cap) pos = atomicAdd(s_cnt, cnt);
+    const int fit = max(0, min(cnt, p.cap - pos));
+    float ws[4] = {sent, sent, sent, sent};
+    int w = 0;
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+        if (m & (1u << r)) {
+            if (w < fit) cand[pos + w] = make_raw(xs[r], col0 + r);
+            else ws[r] = xs[r];  // no room: the slot keeps its value for the next pass
+            w++;
+        }
+    sts128(a, make_float4(ws[0], ws[1], ws[2], ws[3]));
+    return fit == cnt;
+}
+
 template <int NT, int KIND>
 __device__ __forceinline__ int drain_pass(const KnnDev &p, const FastRow &fr, unsigned acc32, int base, int width,
                                           float lo, u64 *cand, int *s_cnt, int *s_overflow, int resume) {
     const float sent = __uint_as_float(kSentinelBits);
+    const float4 sent4 = make_float4(sent, sent, sent, sent);
+    constexpr int S = NT * 4;
+    const float lc = lo * fr.cC, la = lo * fr.A0;
+    const bool filter = !p.exact_only;
+    const bool useT = filter && (KIND == KIND_T || (KIND == KIND_GEN && p.l1 != 0.f));
+    const bool useC = filter && (KIND == KIND_C || (KIND == KIND_GEN && p.l2 != 0.f));
+    const bool useD = filter && (KIND == KIND_D || (KIND == KIND_GEN && p.l3 != 0.f));
+    const int wv = min(width, (p.n_cols - base) & ~3);  // quads below wv lie inside the matrix: float4 loads of Y are safe
     int idx = resume;
-    for (; idx < width; idx += NT * 4) {  // W % 128 == 0: the quad stays inside the panel
-        const unsigned a = acc32 + (unsigned)idx * 4u;
-        const float4 a4 = lds128(a);
-        const float xs[4] = {a4.x, a4.y, a4.z, a4.w};
-        const int col0 = base + idx;
-        bool sv[4] = {true, true, true, true};
-        if (!p.exact_only) {
-            if (KIND == KIND_RAW) {
+    for (; idx < wv; idx += kDrainUnroll * S) {  // W % 128 == 0: a quad stays inside the panel
+        float4 x[kDrainUnroll], yt[kDrainUnroll], yc[kDrainUnroll], yd[kDrainUnroll];
 #pragma unroll
-                for (int r = 0; r < 4; r++) sv[r] = !(xs[r] < lo);
-            } else if (KIND == KIND_C) {
-                const float4 y = load_y4(p.Yc, col0, p.n_cols);
-                const float ys[4] = {y.x, y.y, y.z, y.w};
-#pragma unroll
-                for (int r = 0; r < 4; r++) {
-                    const float den = fmaf(fr.cC, ys[r], fr.A0);
-                    sv[r] = !(den > 0.f && xs[r] < lo * den);
-                }
-            } else {
-                float den[4] = {fr.A0, fr.A0, fr.A0, fr.A0};
-                float sab[4] = {0.f, 0.f, 0.f, 0.f};
-                if (KIND == KIND_T || (KIND == KIND_GEN && p.l1 != 0.f)) {
-                    const float4 y = load_y4(p.Yt, col0, p.n_cols);
-                    const float ys[4] = {y.x, y.y, y.z, y.w};
-#pragma unroll
-                    for (int r = 0; r < 4; r++) {
-                        const float u = fr.cT * ys[r], w = fr.cX * xs[r];
-                        den[r] += u + w;
-                        sab[r] += fabsf(u) + fabsf(w);
-                    }
-                }
-                if (KIND == KIND_GEN && p.l2 != 0.f) {
-                    const float4 y = load_y4(p.Yc, col0, p.n_cols);
-                    const float ys[4] = {y.x, y.y, y.z, y.w};
-#pragma unroll
-                    for (int r = 0; r < 4; r++) {
-                        const float u = fr.cC * ys[r];
-                        den[r] += u;
-                        sab[r] += fabsf(u);
-                    }
-                }
-                if (KIND == KIND_D || (KIND == KIND_GEN && p.l3 != 0.f)) {
-                    const float4 y = load_y4(p.Yd, col0, p.n_cols);
-                    const float ys[4] = {y.x, y.y, y.z, y.w};
-#pragma unroll
-                    for (int r = 0; r < 4; r++) {
-                        const float u = fr.cD * ys[r];
-                        den[r] += u;
-                        sab[r] += fabsf(u);
-                    }
-                }
-#pragma unroll
-                for (int r = 0; r < 4; r++) {
-                    // den huge / inf: lo * den is +-inf or NaN and the comparison does the right thing
-                    const bool rej = den[r] > 0.f && xs[r] < lo * den[r] && (den[r] * 64.f >= sab[r] + fabsf(fr.A0));
-                    sv[r] = !rej;
-                }
+        for (int q = 0; q < kDrainUnroll; q++) {
+            const int i = idx + q * S;
+            yt[q] = sent4; yc[q] = sent4; yd[q] = sent4;
+            if (i < wv) {
+                x[q] = lds128(acc32 + (unsigned)i * 4u);
+                if (useT) yt[q] = __ldg(reinterpret_cast<const float4 *>(p.Yt + base + i));
+                if (useC) yc[q] = __ldg(reinterpret_cast<const float4 *>(p.Yc + base + i));
+                if (useD) yd[q] = __ldg(reinterpret_cast<const float4 *>(p.Yd + base + i));
             }
         }
-        float ws[4] = {sent, sent, sent, sent};
-        bool full = false;
-        if (sv[0] | sv[1] | sv[2] | sv[3]) {
 #pragma unroll
-            for (int r = 0; r < 4; r++)
-                if (sv[r] && __float_as_uint(xs[r]) != kSentinelBits && !push_raw(cand, s_cnt, p.cap, xs[r], col0 + r)) {
-                    ws[r] = xs[r];
-                    full = true;
-                }
+        for (int q = 0; q < kDrainUnroll; q++) {
+            const int i = idx + q * S;
+            if (i >= wv) break;
+            const unsigned a = acc32 + (unsigned)i * 4u;
+            // the common case: nothing in the quad can enter the result (an untouched slot holds -0.0f and is
+            // rejected like any small dot product once lo > 0)
+            if (filter && quad_rejected<KIND>(p, fr, lo, lc, la, x[q], yt[q], yc[q], yd[q])) {
+                sts128(a, sent4);
+                continue;
+            }
+            if (!drain_quad_slow<KIND>(p, fr, filter, lo, a, base + i, x[q], yt[q], yc[q], yd[q], cand, s_cnt)) {
+                *s_overflow = 1;
+                return i;  // resume at this quad
+            }
         }
-        sts128(a, make_float4(ws[0], ws[1], ws[2], ws[3]));
-        if (full) { *s_overflow = 1; break; }
+    }
+    // the last, partial quad of the matrix (n_cols % 4 slots of the last panel): one thread, scalar Y loads
+    if (wv < width && idx != kDrainDone && ((wv >> 2) % NT) == (int)threadIdx.x) {
+        const unsigned a = acc32 + (unsigned)wv * 4u;
+        const float4 x = lds128(a);
+        float4 yt = sent4, yc = sent4, yd = sent4;
+        if (useT) yt = load_y4(p.Yt, base + wv, p.n_cols);
+        if (useC) yc = load_y4(p.Yc, base + wv, p.n_cols);
+        if (useD) yd = load_y4(p.Yd, base + wv, p.n_cols);
+        if (!drain_quad_slow<KIND>(p, fr, filter, lo, a, base + wv, x, yt, yc, yd, cand, s_cnt)) {
+            *s_overflow = 1;
+            return wv;
+        }
+        return kDrainDone;
     }
     return idx;
 }
@@ -422,6 +583,17 @@ struct ExpandArgs {  // what the expansion needs of KnnDev, by value: the routin
     const uint2 *b_pairs;
     int split_stride, n_panels, pn;
 };
+#ifndef SPY_PHASE_TIMING
+#define SPY_PHASE_TIMING 0
+#endif
+#if SPY_PHASE_TIMING
+#define SPY_TICK(id) do { if (tid == 0) { const long long _t = clock64(); ph[id] += _t - t_last; t_last = _t; } } while (0)
+#else
+#define SPY_TICK(id) do { } while (0)
+#endif
+#ifndef SPY_PREFETCH
+#define SPY_PREFETCH 1
+#endif
 #ifndef SPY_BATCH_CAS
 #define SPY_BATCH_CAS 0
 #endif
@@ -465,9 +637,17 @@ __device__ __forceinline__ void smem_add_batch(const unsigned (&addr)[N], const 
 #endif
 }
 
+// Bounds of a group's FIRST segment in the NEXT panel, fetched while the current panel is being accumulated
+// and kept in two registers across the drain: the next accumulation then starts without the dependent
+// "split point -> pairs" chain from DRAM (its pairs have been pulled into L2 as well).
+struct NextFirst {
+    int s, e;
+    bool valid;
+};
+
 template <int NT, int G>
 __device__ __forceinline__ bool accumulate_chunk(const ExpandArgs x, int n, const int *st_u, const float *st_v,
-                                              unsigned accb32) {
+                                                 unsigned accb32, const NextFirst pre, bool want_next, NextFirst &nxt) {
     constexpr int GROUPS = NT / G;
     constexpr int U = unroll_for(NT);  // 16-byte loads (2 pairs each) in flight per lane
     const int tid = threadIdx.x;
@@ -475,13 +655,13 @@ __device__ __forceinline__ bool accumulate_chunk(const ExpandArgs x, int n, cons
     const int grp0 = (tid & ~31) / G;  // first group of this warp: the loop below is warp-uniform
     int idx = tid / G;
     bool any = false;
-    int s = 0, e = 0, s2, e2;
-    float v = 0.f, v2;
-    auto fetch = [&](int i, int &s_, int &e_, float &v_) {
-        s_ = 0; e_ = 0; v_ = 0.f;
+    // software pipeline over the group's entries: the bounds of entry i + 2 are being fetched and the pairs of
+    // entry i + 1 are on their way into L2 while the pairs of entry i are gathered and accumulated
+    int s = 0, e = 0, s1, e1, s2, e2;
+    auto fetch = [&](int i, int &s_, int &e_) {
+        s_ = 0; e_ = 0;
         if (i < n) {
             const int u = st_u[i];
-            v_ = st_v[i];
             if (x.n_panels == 1) { s_ = __ldg(x.b_indptr + u); e_ = __ldg(x.b_indptr + u + 1); }
             else {
                 const int *sp = x.b_split + (size_t)u * x.split_stride + x.pn;
@@ -489,9 +669,23 @@ __device__ __forceinline__ bool accumulate_chunk(const ExpandArgs x, int n, cons
             }
         }
     };
-    fetch(idx, s, e, v);
+    auto prefetch_l2 = [&](int s_, int e_) {  // lane l pulls line l of the segment (G lines cover G * 16 pairs)
+#if SPY_PREFETCH
+        const char *nb = reinterpret_cast<const char *>(x.b_pairs + s_) + 128 * gl;
+        if (nb < reinterpret_cast<const char *>(x.b_pairs + e_)) asm volatile("prefetch.global.L2 [%0];" ::"l"(nb));
+#endif
+    };
+    if (pre.valid) { s = pre.s; e = pre.e; }
+    else fetch(idx, s, e);
+    fetch(idx + GROUPS, s1, e1);
+    int e_far = 0;  // end of the first entry's segment in the next panel (its begin is this panel's end)
+    if (want_next && idx < n) e_far = __ldg(x.b_split + (size_t)st_u[idx] * x.split_stride + x.pn + 2);
+    nxt.s = e; nxt.valid = want_next;
+    bool first_pass = true;
     for (int i0 = grp0; i0 < n; i0 += GROUPS) {
-        fetch(idx + GROUPS, s2, e2, v2);
+        fetch(idx + 2 * GROUPS, s2, e2);
+        if (!first_pass) prefetch_l2(s1, e1);  // its bounds were fetched a whole pass ago
+        const float v = (idx < n) ? st_v[idx] : 0.f;
         const int sa = s & ~1;  // pairs are 8 bytes: an even position is 16-byte aligned
         const int maxspan = __reduce_max_sync(0xffffffffu, e - sa);
         any |= e > s;
@@ -516,9 +710,12 @@ __device__ __forceinline__ bool accumulate_chunk(const ExpandArgs x, int n, cons
             }
             smem_add_batch<2 * U>(addr, val, pend);
         }
-        s = s2; e = e2; v = v2;
+        if (first_pass) { prefetch_l2(s1, e1); first_pass = false; }
+        s = s1; e = e1; s1 = s2; e1 = e2;
         idx += GROUPS;
     }
+    nxt.e = e_far;
+    if (want_next) prefetch_l2(nxt.s, nxt.e);
     return any;
 }
 
@@ -532,7 +729,7 @@ __device__ __forceinline__ bool accumulate_chunk(const ExpandArgs x, int n, cons
 //             (dot product, column) and evaluated densely afterwards -- computeSimilarity with its IEEE
 //             division runs with all lanes busy -- then the sampled selection keeps the best k.
 template <int NT, int KIND, bool CAND_SMEM, int G>
-__global__ void __launch_bounds__(NT, 1)
+__global__ void __launch_bounds__(NT, 1024 / NT)
 knn_flat_kernel(const __grid_constant__ KnnDev p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *acc = reinterpret_cast<float *>(smem_raw);
@@ -541,13 +738,15 @@ knn_flat_kernel(const __grid_constant__ KnnDev p) {
     if (CAND_SMEM) { cand = reinterpret_cast<u64 *>(ptr); ptr += (size_t)p.cap * sizeof(u64); }
     else cand = p.cand_global + (size_t)blockIdx.x * p.cap;
     // staged chunk of the target row (8 bytes per thread); the same bytes serve as the selection's scratch
-    // (`tmp`), so a selection invalidates the staged row (staged_ok)
+    // (`tmp`), so a selection invalidates the staged row (staged_c0)
+    constexpr int CH = stage_entries(NT);                    // entries of the target row staged at a time
     int *st_u = reinterpret_cast<int *>(ptr);               // A's column ids = rows of B
-    float *st_v = reinterpret_cast<float *>(st_u + NT);     // A's values
+    float *st_v = reinterpret_cast<float *>(st_u + CH);     // A's values
     u64 *tmp = reinterpret_cast<u64 *>(ptr);
-    constexpr int kTmpCap = NT;
+    constexpr int kTmpCap = CH;
 
-    __shared__ int s_row, s_cnt, s_overflow, s_live;
+    __shared__ int s_cnt, s_overflow, s_live;
+    __shared__ int s_next[5];  // the NEXT row of this CTA: queue slot, output position, row id, A-row begin / end
     __shared__ u64 s_tau, s_pivot;
 
     const int tid = threadIdx.x;
@@ -556,28 +755,58 @@ knn_flat_kernel(const __grid_constant__ KnnDev p) {
     const unsigned acc32 = (unsigned)__cvta_generic_to_shared(acc);
 
     for (int i = tid * 4; i < p.W; i += NT * 4) *reinterpret_cast<float4 *>(acc + i) = sentinel4;
+#if SPY_PHASE_TIMING
+    long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long t_last = clock64();
+    __shared__ unsigned long long s_busy;
+    if (tid == 0) s_busy = 0ull;
+#endif
+
+    // Rows are claimed one ahead (the reference's `omp for schedule(dynamic)`, s_plus.h:337): thread 0 resolves the
+    // next row's queue slot -> row id -> A-row bounds while the other warps are still accumulating, and every
+    // thread loads its entry of that A row into registers before the current row's last drain, so that a row
+    // starts without a chain of dependent global loads.
+    auto claim_next = [&]() {
+        const int slot = atomicAdd(p.work_counter, 1);
+        int i_out = 0, t = 0, b = 0, e = 0;
+        if (slot < p.n_targets) {
+            i_out = p.row_order ? __ldg(p.row_order + slot) : slot;
+            t = __ldg(p.targets + i_out);
+            b = __ldg(p.a_indptr + t);
+            e = __ldg(p.a_indptr + t + 1);
+        }
+        s_next[0] = slot; s_next[1] = i_out; s_next[2] = t; s_next[3] = b; s_next[4] = e;
+    };
+    int u_n = 0;
+    float v_n = 0.f;
+    auto load_next_entries = [&]() {  // first chunk of the next row -> registers
+        if (s_next[0] < p.n_targets) {
+            const int b = s_next[3], e = s_next[4];
+            if (tid < e - b) { u_n = __ldg(p.a_indices + b + tid); v_n = __ldg(p.a_data + b + tid); }
+        }
+    };
+    if (tid == 0) claim_next();
+    __syncthreads();
+    load_next_entries();
 
     for (;;) {
-        __syncthreads();
-        if (tid == 0) { s_row = atomicAdd(p.work_counter, 1); s_cnt = 0; s_tau = 0ull; s_overflow = 0; }
-        __syncthreads();
-        const int slot = s_row;
+        const int slot = s_next[0];
         if (slot >= p.n_targets) break;
-        const int i_out = p.row_order ? __ldg(p.row_order + slot) : slot;
-        const int t = __ldg(p.targets + i_out);
-        const int a0 = __ldg(p.a_indptr + t), a1 = __ldg(p.a_indptr + t + 1);
-        const bool single_chunk = (a1 - a0) <= NT;
-        bool staged_ok = false;
+        const int i_out = s_next[1], t = s_next[2], a0 = s_next[3], a1 = s_next[4];
+        if (tid < a1 - a0) { st_u[tid] = u_n; st_v[tid] = v_n; }  // entries [0, NT) of the first chunk come from registers
+        if (tid + NT < min(a1 - a0, CH)) {                        // its tail, if the row is that long, from memory
+            st_u[tid + NT] = __ldg(p.a_indices + a0 + NT + tid);
+            st_v[tid + NT] = __ldg(p.a_data + a0 + NT + tid);
+        }
+        __syncthreads();  // the staged chunk is visible; s_next and the previous row's s_cnt have been read by everyone
+        if (tid == 0) { s_cnt = 0; s_tau = 0ull; s_overflow = 0; }  // first read after the accumulation's barrier
+        SPY_TICK(7);
+        int staged_c0 = a0;  // which chunk of the A row the staging area holds (-1: none)
+        NextFirst pre = {0, 0, false};
         SimRow sr;
         sr.Xt = (p.l1 != 0.f) ? __ldg(p.Xt + t) : 0.f;
         sr.Xc = (p.l2 != 0.f) ? __ldg(p.Xc + t) : 0.f;
         sr.Xd = (p.l3 != 0.f) ? __ldg(p.Xd + t) : 0.f;
-        FastRow fr;
-        fr.A0 = p.stab + p.l1 * p.t1 * sr.Xt;
-        fr.cT = p.l1 * p.t2;
-        fr.cX = p.l1 * (1.f - p.t1 - p.t2);
-        fr.cC = p.l2 * sr.Xc;
-        fr.cD = p.l3 * sr.Xd;
         u64 tau = 0ull;
         float lo = reject_bound(p, tau);
         int n_eval = 0;  // cand[0, n_eval) are evaluated keys, cand[n_eval, s_cnt) raw candidates (uniform)
@@ -587,20 +816,42 @@ knn_flat_kernel(const __grid_constant__ KnnDev p) {
             const int width = min(p.W, p.n_cols - base);
             const unsigned accb32 = acc32 - (unsigned)base * 4u;  // &acc[col - base] == accb32 + 4 * col
             bool any = false;
+#if SPY_PHASE_TIMING
+            const long long t_acc0 = clock64();
+#endif
             // ---------------- expand + accumulate (s_plus.h:358-403 / 418-438) ----------------
-            for (int c0 = a0; c0 < a1; c0 += NT) {
-                const int n = min(NT, a1 - c0);
-                if (!staged_ok) {
+            for (int c0 = a0; c0 < a1; c0 += CH) {
+                const int n = min(CH, a1 - c0);
+                if (staged_c0 != c0) {
+                    SPY_TICK(1);
                     __syncthreads();  // earlier readers of the staging area (previous chunk / selection scratch)
-                    if (tid < n) { st_u[tid] = __ldg(p.a_indices + c0 + tid); st_v[tid] = __ldg(p.a_data + c0 + tid); }
+                    for (int i = tid; i < n; i += NT) { st_u[i] = __ldg(p.a_indices + c0 + i); st_v[i] = __ldg(p.a_data + c0 + i); }
                     __syncthreads();
-                    staged_ok = single_chunk;
+                    staged_c0 = c0;
+                    SPY_TICK(0);
                 }
                 const ExpandArgs x = {p.b_indptr, p.b_split, p.b_pairs, p.split_stride, p.n_panels, pn};
-                any |= accumulate_chunk<NT, G>(x, n, st_u, st_v, accb32);
+                const bool first = c0 == a0;  // the cross-panel prefetch covers the first chunk of the row
+                NextFirst none = {0, 0, false}, got = none;
+                any |= accumulate_chunk<NT, G>(x, n, st_u, st_v, accb32, first ? pre : none,
+                                               first && pn + 1 < p.n_panels, got);
+                if (first) pre = got;
             }
+            if (pn == 0 && tid == 0) claim_next();  // hidden behind the other warps' accumulation
+#if SPY_PHASE_TIMING
+            if ((tid & 31) == 0 && a1 > a0) atomicAdd(&s_busy, (unsigned long long)(clock64() - t_acc0));
+#endif
             // barrier: all adds have landed; nothing landed in this panel => accumulator still clean
-            if (!__syncthreads_or(any ? 1 : 0)) continue;
+            const int landed = __syncthreads_or(any ? 1 : 0);
+            SPY_TICK(1);
+            if (pn == p.n_panels - 1) load_next_entries();  // in flight during the last drain + final selection
+            if (!landed) continue;
+            FastRow fr;
+            fr.A0 = p.stab + p.l1 * p.t1 * sr.Xt;
+            fr.cT = p.l1 * p.t2;
+            fr.cX = p.l1 * (1.f - p.t1 - p.t2);
+            fr.cC = p.l2 * sr.Xc;
+            fr.cD = p.l3 * sr.Xd;
 
             // ---------------- per-row filter matrix: erase filtered columns (s_plus.h:159-172) --
             if (p.filter_mode == SPY_SEL_MATRIX) {
@@ -623,6 +874,7 @@ knn_flat_kernel(const __grid_constant__ KnnDev p) {
                 if (p.target_mode == SPY_SEL_MATRIX) drain_pass_list<NT>(p, acc, base, tlo, thi, cand, &s_cnt, &s_overflow);
                 else resume = drain_pass<NT, KIND>(p, fr, acc32, base, width, lo, cand, &s_cnt, &s_overflow, resume);
                 __syncthreads();
+                SPY_TICK(3);
                 const bool again = s_overflow != 0;
                 const int cnt = min(s_cnt, p.cap);
                 // exact values of the raw candidates, all lanes busy (computeSimilarity, s_plus.h:129-156, 206)
@@ -636,13 +888,15 @@ knn_flat_kernel(const __grid_constant__ KnnDev p) {
                 }
                 n_eval = cnt;
                 __syncthreads();
+                SPY_TICK(4);
                 if (again || cnt > p.cap / 2) {  // tighten tau while the buffer is reasonably full
                     if (tid == 0) s_overflow = 0;
-                    select_topk<NT>(cand, cnt, p.k, tmp, kTmpCap, &s_cnt, &s_tau, &s_live, &s_pivot);
-                    staged_ok = false;  // tmp overlays the staged row
+                    tighten_topk<NT>(cand, cnt, p.k, tmp, kTmpCap, &s_cnt, &s_tau, &s_live, &s_pivot);
+                    staged_c0 = -1;  // tmp overlays the staged row
                     tau = s_tau;
                     lo = reject_bound(p, tau);
                     n_eval = s_cnt;
+                    SPY_TICK(5);
                 }
                 if (!again) break;
             }
@@ -669,7 +923,15 @@ knn_flat_kernel(const __grid_constant__ KnnDev p) {
             if (p.out_rows) p.out_rows[o + j] = row;
         }
         if (tid == 0 && p.out_counts) p.out_counts[i_out] = n_out;
+        SPY_TICK(6);
     }
+#if SPY_PHASE_TIMING
+    __syncthreads();
+    if (tid == 0) {
+        ph[2] = (long long)(s_busy / (NT / 32));  // mean over warps of "cycles from the end of staging to the warp's own end"
+        for (int i = 0; i < 8; i++) atomicAdd(p.phase + i, (u64)ph[i]);
+    }
+#endif
 }
 
 typedef void (*knn_kernel_t)(const KnnDev);
