@@ -21,10 +21,15 @@ job = _engine.prepare_job(urm.T, None, l2=1.0, c1=0.5, c2=0.5, k=100, verbose=Fa
 for it in range(2):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(); job.run(); ev1.record(); torch.cuda.synchronize()
-    ph = job.scratch[128:192].view(torch.int64).cpu().tolist()
-names = ["stage", "accumulate (wall, to barrier)", "accumulate (mean warp busy)", "drain pass", "evaluate", "tighten", "final select + write", "row fetch / other"]
-wall = [ph[i] for i in (0, 1, 3, 4, 5, 6, 7)]
+    ph = job.scratch[128:256].view(torch.int64).cpu().tolist()
+names = ["stage", "accumulate (wall, to barrier)", "accumulate (mean warp busy)", "drain barrier wait, panel 0", "evaluate", "tighten",
+         "final select + write", "row fetch / other", "drain barrier wait, panels >= 1", "#drain passes panel 0 (x CTAs)", "#drain passes panels >= 1",
+         "drain scan (thread 0), panel 0", "drain scan (thread 0), panels >= 1", "post-accumulate (next-row loads issue)"]
+wall = [ph[i] for i in (0, 1, 3, 4, 5, 6, 7, 8, 11, 12, 13)]
 tot = sum(wall)
 print(f"kernel {ev0.elapsed_time(ev1):.1f} ms; plan panels={job.args.n_panels} W={job.args.panel_width} threads={job.args.threads} group={job.args.group}")
-for n, v in zip(names, ph):
-    print(f"  {n:32s} {100.0 * v / tot:6.2f} %")
+for i, (n, v) in enumerate(zip(names, ph)):
+    if i in (9, 10):
+        print(f"  {n:40s} {v} passes = {v / (200000 * scale):.2f} per row")
+    else:
+        print(f"  {n:40s} {100.0 * v / tot:6.2f} %")

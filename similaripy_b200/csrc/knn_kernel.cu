@@ -39,6 +39,18 @@ __global__ void pack_pairs_kernel(long long nnz, const int *__restrict__ indices
         pairs[q] = make_uint2((unsigned)indices[q], __float_as_uint(data[q]));
 }
 
+// out[b] = min of y over columns [128 b, 128 b + 128): the drain's coarse bound (one warp per block)
+__global__ void block_min_kernel(int n, const float *__restrict__ y, float *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int blk = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
+    if (blk * 128 >= n) return;
+    float m = __int_as_float(0x7f800000);
+    for (int i = blk * 128 + lane; i < min(n, blk * 128 + 128); i += 32) m = fminf(m, y[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) out[blk] = m;
+}
+
 // split[u*stride + pn] = first q in row u with b_indices[q] >= pn*W
 __global__ void build_split_kernel(int b_rows, const int *__restrict__ b_indptr, const int *__restrict__ b_indices,
                                    int W, int n_panels, int stride, int *__restrict__ split) {
@@ -143,6 +155,8 @@ static int similarity_kind(const spy_knn_args &a, int &exact_only) {
     return KIND_GEN;
 }
 
+static int64_t block_min_bytes(int n_cols) { return (((int64_t)(std::max(n_cols, 1) + 127) / 128) * 4 + 255) / 256 * 256; }
+
 static int grid_size(const Plan &pl, int n_targets, int device) {
     DeviceInfo di = device_info(device);
     long long g = (long long)di.sm_count * pl.ctas_per_sm;
@@ -175,7 +189,7 @@ int64_t spy_knn_scratch_bytes(const spy_knn_args *args, int device) {
     if (!args) return SPY_ERR_INVALID;
     Plan pl;
     if (make_plan(*args, device, pl) != SPY_OK) return SPY_ERR_INVALID;
-    int64_t bytes = 256;  // work counter
+    int64_t bytes = 256 + block_min_bytes(args->n_cols);  // work counter (+ phase counters), per-block minima of Y
     if (!pl.cand_smem) bytes += (int64_t)grid_size(pl, std::max(args->n_targets, 1), device) * pl.cap * 8;
     return bytes;
 }
@@ -228,7 +242,8 @@ int spy_knn_topk_dev(const spy_knn_args *args, void *scratch, int64_t scratch_by
     int rc = make_plan(a, device, pl);
     if (rc != SPY_OK) return rc;
     const int grid = grid_size(pl, a.n_targets, device);
-    int64_t need = 256 + (pl.cand_smem ? 0 : (int64_t)grid * pl.cap * 8);
+    const int64_t bm_bytes = block_min_bytes(a.n_cols);
+    int64_t need = 256 + bm_bytes + (pl.cand_smem ? 0 : (int64_t)grid * pl.cap * 8);
     SPY_REQUIRE(scratch != nullptr && scratch_bytes >= need, "scratch too small: need %lld bytes", (long long)need);
 
     KnnDev d;
@@ -251,10 +266,20 @@ int spy_knn_topk_dev(const spy_knn_args *args, void *scratch, int64_t scratch_by
     d.out_rows = a.out_rows; d.out_cols = a.out_cols; d.out_vals = a.out_values; d.out_counts = a.out_counts;
     d.work_counter = reinterpret_cast<int *>(scratch);
     d.phase = reinterpret_cast<u64 *>(reinterpret_cast<unsigned char *>(scratch) + 128);
-    d.cand_global = reinterpret_cast<u64 *>(reinterpret_cast<unsigned char *>(scratch) + 256);
+    d.cand_global = reinterpret_cast<u64 *>(reinterpret_cast<unsigned char *>(scratch) + 256 + bm_bytes);
 
     cudaStream_t st = as_stream(stream);
     SPY_CUDA_OK(cudaMemsetAsync(scratch, 0, 256, st));
+    // per-block minima of the one Y vector the drain's coarse bound uses (cosine family: Yc, depop only: Yd)
+    d.y_block_min = nullptr;
+    const float *ysrc = (kind == KIND_C) ? a.Ycosine : (kind == KIND_D) ? a.Ydepop : nullptr;
+    if (ysrc != nullptr && a.n_cols > 0) {
+        float *bm = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(scratch) + 256);
+        const int blocks = (a.n_cols + 127) / 128;
+        block_min_kernel<<<(blocks * 32 + 255) / 256, 256, 0, st>>>(a.n_cols, ysrc, bm);
+        SPY_LAUNCH_OK();
+        d.y_block_min = bm;
+    }
     knn_kernel_t kern = pick_kernel(pl.threads, kind, pl.cand_smem, pl.group);
     SPY_CUDA_OK(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
     kern<<<grid, pl.threads, pl.smem_bytes, st>>>(d);

@@ -45,6 +45,7 @@ struct KnnDev {
     const int *b_split;
     int split_stride, n_panels, W, n_cols;
     const float *Xt, *Yt, *Xc, *Yc, *Xd, *Yd;
+    const float *y_block_min;  // min over every 128 consecutive columns of Yc (cosine family) or Yd (depop only)
     float a1, l1, l2, l3, t1, t2, stab, bayes, thr;
     int has_den;     // any of l1, l2, l3, stab, bayes != 0 (s_plus.h:144)
     int exact_only;  // skip the fast pre-filter (a1 != 1: powf involved)
@@ -81,15 +82,16 @@ __device__ __forceinline__ u64 make_key(float v, int col) {
 struct SimRow {
     float Xt, Xc, Xd;
 };
-__device__ __forceinline__ float similarity_value(const KnnDev &p, const SimRow &r, int col, float xy) {
+// yt / yc / yd = Ytversky / Ycosine / Ydepop of the candidate's column (read only where the weight is non-zero)
+__device__ __forceinline__ float similarity_value(const KnnDev &p, const SimRow &r, float xy, float yt, float yc, float yd) {
     float vT = 0.f, vC = 0.f, vD = 0.f, val = xy;
     if (p.l1 != 0.f) {
         float a = __fmul_rn(p.t1, __fsub_rn(r.Xt, xy));
-        float b = __fmul_rn(p.t2, __fsub_rn(__ldg(p.Yt + col), xy));
+        float b = __fmul_rn(p.t2, __fsub_rn(yt, xy));
         vT = __fmul_rn(p.l1, __fadd_rn(__fadd_rn(a, b), xy));
     }
-    if (p.l2 != 0.f) vC = __fmul_rn(p.l2, __fmul_rn(r.Xc, __ldg(p.Yc + col)));
-    if (p.l3 != 0.f) vD = __fmul_rn(p.l3, __fmul_rn(r.Xd, __ldg(p.Yd + col)));
+    if (p.l2 != 0.f) vC = __fmul_rn(p.l2, __fmul_rn(r.Xc, yc));
+    if (p.l3 != 0.f) vD = __fmul_rn(p.l3, __fmul_rn(r.Xd, yd));
     if (p.a1 != 1.f) xy = powf(xy, p.a1);
     if (p.l1 != 0.f || p.l2 != 0.f || p.l3 != 0.f || p.stab != 0.f || p.bayes != 0.f) {
         float den = __fadd_rn(__fadd_rn(__fadd_rn(vT, vC), vD), p.stab);
@@ -136,7 +138,7 @@ __device__ void bitonic_sort_desc(u64 *cand, int S) {
 // hundred) are compacted into `tmp` and only those are sorted.  If the pivot turns out too high (fewer than
 // k keys above it) or too low (tmp overflows) the full sort runs -- results never depend on the sampling.
 template <int NT>
-__device__ void sort_and_publish(u64 *buf, int n, int k, u64 *cand, int *s_cnt, u64 *s_tau, int *s_live) {
+__device__ __noinline__ void sort_and_publish(u64 *buf, int n, int k, u64 *cand, int *s_cnt, u64 *s_tau, int *s_live) {
     // sort buf[0, n) descending (padded with zeros), copy the best min(k, live) to cand if buf != cand
     const int tid = threadIdx.x;
     int S = 2;
@@ -164,7 +166,7 @@ __device__ void sort_and_publish(u64 *buf, int n, int k, u64 *cand, int *s_cnt, 
 // 36-55 barrier-separated compare-exchange steps of the bitonic network: the cheaper one below ~600 keys.
 // buf must not alias cand.  NT / P threads share one key (P = n rounded up to a power of two >= 32).
 template <int NT>
-__device__ void rank_and_publish(const u64 *buf, int n, int k, u64 *cand, int *s_cnt, u64 *s_tau, int *s_live) {
+__device__ __noinline__ void rank_and_publish(const u64 *buf, int n, int k, u64 *cand, int *s_cnt, u64 *s_tau, int *s_live) {
     const int tid = threadIdx.x;
     int P = 32;
     while (P < n) P <<= 1;
@@ -207,22 +209,32 @@ __device__ void rank_and_publish(const u64 *buf, int n, int k, u64 *cand, int *s
 // distance (3 sigma) below the sample quantile of the k-th best, and the keys above the pivot are compacted
 // into tmp.  Returns their number c (block-uniform); the caller checks k <= c <= tmp_cap.
 template <int NT>
-__device__ int pivot_compact(const u64 *cand, int n, int j, u64 *tmp, int tmp_cap, int *s_live, u64 *s_pivot) {
+__device__ __noinline__ int pivot_compact(const u64 *cand, int n, int j, u64 *tmp, int tmp_cap, int *s_live, u64 *s_pivot) {
     const int tid = threadIdx.x;
-    if (tid < 64) tmp[tid] = cand[(int)(((long long)tid * n) >> 6)];
-    if (tid == 0) *s_live = 0;
-    __syncthreads();
-    if (tid < 32) {  // 64-key bitonic sort by one warp, descending
-        for (int size = 2; size <= 64; size <<= 1)
+    if (tid < 32) {
+        // 64 strided samples, two per lane (element e = lane + 32 r), sorted descending by a bitonic network in
+        // registers: strides below 32 exchange with lane ^ stride, stride 32 is the lane's own pair
+        u64 k0 = cand[(int)(((long long)tid * n) >> 6)];
+        u64 k1 = cand[(int)(((long long)(tid + 32) * n) >> 6)];
+#pragma unroll
+        for (int size = 2; size <= 64; size <<= 1) {
+#pragma unroll
             for (int stride = size >> 1; stride > 0; stride >>= 1) {
-                const int lo = ((tid & ~(stride - 1)) << 1) | (tid & (stride - 1));
-                const int hi = lo + stride;
-                const bool desc = ((lo & size) == 0) || (size == 64);
-                const u64 a = tmp[lo], b = tmp[hi];
-                if ((a < b) == desc) { tmp[lo] = b; tmp[hi] = a; }
-                __syncwarp();
+                if (stride == 32) {
+                    const u64 hi = k0 > k1 ? k0 : k1, lo = k0 > k1 ? k1 : k0;
+                    k0 = hi; k1 = lo;
+                } else {
+                    const u64 o0 = __shfl_xor_sync(0xffffffffu, k0, stride), o1 = __shfl_xor_sync(0xffffffffu, k1, stride);
+                    const bool lower = (tid & stride) == 0;
+                    const bool desc0 = size == 64 || (size == 32 ? true : (tid & size) == 0);   // e = lane
+                    const bool desc1 = size == 64 || (size == 32 ? false : (tid & size) == 0);  // e = lane + 32
+                    k0 = ((k0 > o0) == (lower == desc0)) ? k0 : o0;
+                    k1 = ((k1 > o1) == (lower == desc1)) ? k1 : o1;
+                }
             }
-        if (tid == 0) *s_pivot = tmp[j - 1];
+        }
+        const u64 pv = __shfl_sync(0xffffffffu, (j - 1) < 32 ? k0 : k1, (j - 1) & 31);
+        if (tid == 0) { *s_pivot = pv; *s_live = 0; }
     }
     __syncthreads();
     const u64 pivot = *s_pivot;
@@ -392,24 +404,6 @@ __device__ __forceinline__ void sts128(unsigned addr, float4 v) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-// raw (not yet evaluated) candidate: accumulated dot product + column
-__device__ __forceinline__ u64 make_raw(float xy, int col) { return ((u64)__float_as_uint(xy) << 32) | (u64)(unsigned)col; }
-
-// Buffer one raw candidate; false when the buffer is full (the caller then leaves the slot as it is).
-__device__ __forceinline__ bool push_raw(u64 *cand, int *s_cnt, int cap, float xy, int col) {
-    if (*reinterpret_cast<volatile int *>(s_cnt) >= cap) return false;
-    const int pos = atomicAdd(s_cnt, 1);
-    if (pos >= cap) return false;
-    cand[pos] = make_raw(xy, col);
-    return true;
-}
-
-// One drain pass over the current panel, 4 slots per thread per step (LDS.128 / STS.128).  No barriers inside.
-// Every slot visited is reset to "untouched" unless it survived the pre-filter and the candidate buffer was
-// full; in that case the thread raises *s_overflow and stops, and the index it returns is where it resumes
-// after the caller has evaluated + selected (which raises tau), so no slot is scanned twice.
-// An untouched slot holds -0.0f: with lo > 0 it fails "x >= lo * den" like any small dot product, so the
-// common path needs no separate "touched" test -- only survivors are checked against the sentinel.
 // "this slot cannot enter the result": x < lo * den for den safely positive (see above)
 template <int KIND>
 __device__ __forceinline__ bool slot_rejected(const KnnDev &p, const FastRow &fr, float x, float lo, float yt, float yc,
@@ -439,120 +433,145 @@ __device__ __forceinline__ bool slot_rejected(const KnnDev &p, const FastRow &fr
     return den > 0.f && x < lo * den && den * 64.f >= sab;
 }
 
-// the four slots of a quad at once; KIND_C and KIND_RAW fold the bound into one FFMA + compare per slot:
-// x < lo * (cC * y + A0)  ==  x < (lo * cC) * y + lo * A0  (den >= 0 for these kinds: norms and shrink are
-// non-negative; the regrouping moves the bound by a few ulp, far inside its 1e-4 safety margin)
+// Survivors of a quad as a 4-bit mask: touched slots the pre-filter cannot reject.  KIND_C and KIND_RAW fold the
+// bound into one FFMA + compare per slot:  x < lo * (cC * y + A0)  ==  x < (lo * cC) * y + lo * A0  (den >= 0 for
+// these kinds: norms and shrink are non-negative; the regrouping moves the bound by a few ulp, far inside its
+// 1e-4 safety margin).  An untouched slot holds -0.0f.
 template <int KIND>
-__device__ __forceinline__ bool quad_rejected(const KnnDev &p, const FastRow &fr, float lo, float lc, float la,
-                                              const float4 &x, const float4 &yt, const float4 &yc, const float4 &yd) {
-    if (KIND == KIND_RAW) return (x.x < lo) & (x.y < lo) & (x.z < lo) & (x.w < lo);
-    if (KIND == KIND_C)
-        return (x.x < fmaf(lc, yc.x, la)) & (x.y < fmaf(lc, yc.y, la)) & (x.z < fmaf(lc, yc.z, la)) & (x.w < fmaf(lc, yc.w, la));
-    return slot_rejected<KIND>(p, fr, x.x, lo, yt.x, yc.x, yd.x) & slot_rejected<KIND>(p, fr, x.y, lo, yt.y, yc.y, yd.y) &
-           slot_rejected<KIND>(p, fr, x.z, lo, yt.z, yc.z, yd.z) & slot_rejected<KIND>(p, fr, x.w, lo, yt.w, yc.w, yd.w);
-}
-
-constexpr int kDrainDone = 0x3fffffff;  // resume index of a thread that has also finished the partial last quad
-#ifndef SPY_DRAIN_UNROLL
-#define SPY_DRAIN_UNROLL 1
-#endif
-constexpr int kDrainUnroll = SPY_DRAIN_UNROLL;  // quads a thread has in flight: their Y vectors come from L2 (227 KB of
-                                                // shared memory leave no L1)
-
-// Survivors of one quad: touched slots that pass the per-slot filter are buffered; a slot that does not fit keeps its
-// value.  Returns false when the buffer was full.
-template <int KIND>
-__device__ __forceinline__ bool drain_quad_slow(const KnnDev &p, const FastRow &fr, bool filter, float lo, unsigned a, int col0,
-                                                const float4 &x, const float4 &yt, const float4 &yc, const float4 &yd,
-                                                u64 *cand, int *s_cnt) {
-    const float sent = __uint_as_float(kSentinelBits);
+__device__ __forceinline__ unsigned survivor_mask(const KnnDev &p, const FastRow &fr, bool filter, float lo, float lc, float la,
+                                                  const float4 &x, const float4 &yt, const float4 &yc, const float4 &yd) {
     const float xs[4] = {x.x, x.y, x.z, x.w};
     const float yts[4] = {yt.x, yt.y, yt.z, yt.w}, ycs[4] = {yc.x, yc.y, yc.z, yc.w}, yds[4] = {yd.x, yd.y, yd.z, yd.w};
-    unsigned m = 0u;  // the quad's survivors
+    unsigned m = 0u;
 #pragma unroll
-    for (int r = 0; r < 4; r++)
-        if (__float_as_uint(xs[r]) != kSentinelBits && !(filter && slot_rejected<KIND>(p, fr, xs[r], lo, yts[r], ycs[r], yds[r])))
-            m |= 1u << r;
-    if (m == 0u) {
-        sts128(a, make_float4(sent, sent, sent, sent));
-        return true;
+    for (int r = 0; r < 4; r++) {
+        bool rej = false;
+        if (filter) {
+            if (KIND == KIND_RAW) rej = xs[r] < lo;
+            else if (KIND == KIND_C) rej = xs[r] < fmaf(lc, ycs[r], la);
+            else rej = slot_rejected<KIND>(p, fr, xs[r], lo, yts[r], ycs[r], yds[r]);
+        }
+        if (!rej && __float_as_uint(xs[r]) != kSentinelBits) m |= 1u << r;
     }
-    // one reservation for all of them (a thread-level atomic: the few lanes with survivors serialise on s_cnt)
+    return m;
+}
+
+// raw (not yet evaluated) candidate: accumulated dot product + column
+__device__ __forceinline__ u64 make_raw(float xy, int col) { return ((u64)__float_as_uint(xy) << 32) | (u64)(unsigned)col; }
+
+// Buffer the survivors `m` of a quad RAW (dot product, column) with ONE reservation; their exact value is computed
+// afterwards for the whole buffer with all lanes busy (the IEEE division of computeSimilarity would otherwise run
+// with one or two lanes of a warp active).  A survivor that does not fit keeps its slot value.  Returns false
+// when the buffer was full.
+__device__ __forceinline__ bool push_quad(int cap, unsigned a, int col0, const float4 &x, unsigned m, u64 *cand, int *s_cnt) {
+    const float sent = __uint_as_float(kSentinelBits);
+    const float xs[4] = {x.x, x.y, x.z, x.w};
     const int cnt = __popc(m);
-    int pos = p.cap;
-    if (*reinterpret_cast<volatile int *>(s_cnt) < p.cap) pos = atomicAdd(s_cnt, cnt);
-    const int fit = max(0, min(cnt, p.cap - pos));
+    int pos = cap;
+    if (*reinterpret_cast<volatile int *>(s_cnt) < cap) pos = atomicAdd(s_cnt, cnt);  // few lanes: they serialise on s_cnt
+    const int fit = max(0, min(cnt, cap - pos));
     float ws[4] = {sent, sent, sent, sent};
-    int w = 0;
 #pragma unroll
     for (int r = 0; r < 4; r++)
         if (m & (1u << r)) {
+            const int w = __popc(m & ((1u << r) - 1u));
             if (w < fit) cand[pos + w] = make_raw(xs[r], col0 + r);
-            else ws[r] = xs[r];  // no room: the slot keeps its value for the next pass
-            w++;
+            else ws[r] = xs[r];
         }
     sts128(a, make_float4(ws[0], ws[1], ws[2], ws[3]));
     return fit == cnt;
 }
 
+// One drain pass over the current panel, in two phases.  A thread owns the quads tid + it * NT (it = 0, 1, ...: at
+// most 14 steps); a warp's 32 quads of one step are the 128 consecutive columns of one block of the per-block
+// minima of Y (y_block_min).
+//   phase 1 (no global loads): if x < lo * (c * min_block(Y) + A0) for the four slots of a quad, nothing in it can
+//           enter the result and it is reset to "untouched"; the other quads are only FLAGGED (one bit per step);
+//   phase 2: the flagged quads load their Y vectors -- from L2: 227 KB of shared memory leave no L1 -- a batch at
+//           a time, so that a thread (and with it the warp) waits once per batch, not once per quad; the per-slot
+//           test then buffers the survivors.
+// `todo` is the thread's set of steps still to drain (bit it); the pass returns what is left of it when the
+// candidate buffer filled up (*s_overflow raised) -- the caller evaluates + selects, which raises tau, and calls
+// again -- else 0.  No block barriers inside.
 template <int NT, int KIND>
-__device__ __forceinline__ int drain_pass(const KnnDev &p, const FastRow &fr, unsigned acc32, int base, int width,
-                                          float lo, u64 *cand, int *s_cnt, int *s_overflow, int resume) {
+__device__ __forceinline__ unsigned drain_pass(const KnnDev &p, const FastRow &fr, unsigned acc32, int base, int width, float lo,
+                                               float yv, u64 *cand, int *s_cnt, int *s_overflow, unsigned todo) {
     const float sent = __uint_as_float(kSentinelBits);
     const float4 sent4 = make_float4(sent, sent, sent, sent);
     constexpr int S = NT * 4;
-    const float lc = lo * fr.cC, la = lo * fr.A0;
+#ifndef SPY_DRAIN_BATCH
+#define SPY_DRAIN_BATCH 2
+#endif
+    constexpr int B = (KIND == KIND_GEN) ? 1 : (KIND == KIND_T ? 2 : SPY_DRAIN_BATCH);  // quads per phase-2 batch (registers)
+    const int tid = threadIdx.x, lane = tid & 31;
     const bool filter = !p.exact_only;
     const bool useT = filter && (KIND == KIND_T || (KIND == KIND_GEN && p.l1 != 0.f));
     const bool useC = filter && (KIND == KIND_C || (KIND == KIND_GEN && p.l2 != 0.f));
     const bool useD = filter && (KIND == KIND_D || (KIND == KIND_GEN && p.l3 != 0.f));
+    // x < lc * y + la is the folded bound of KIND_C (y = Yc) and KIND_D (y = Yd)
+    const float lc = lo * (KIND == KIND_D ? fr.cD : fr.cC), la = lo * fr.A0;
     const int wv = min(width, (p.n_cols - base) & ~3);  // quads below wv lie inside the matrix: float4 loads of Y are safe
-    int idx = resume;
-    for (; idx < wv; idx += kDrainUnroll * S) {  // W % 128 == 0: a quad stays inside the panel
-        float4 x[kDrainUnroll], yt[kDrainUnroll], yc[kDrainUnroll], yd[kDrainUnroll];
-#pragma unroll
-        for (int q = 0; q < kDrainUnroll; q++) {
-            const int i = idx + q * S;
-            yt[q] = sent4; yc[q] = sent4; yd[q] = sent4;
-            if (i < wv) {
-                x[q] = lds128(acc32 + (unsigned)i * 4u);
-                if (useT) yt[q] = __ldg(reinterpret_cast<const float4 *>(p.Yt + base + i));
-                if (useC) yc[q] = __ldg(reinterpret_cast<const float4 *>(p.Yc + base + i));
-                if (useD) yd[q] = __ldg(reinterpret_cast<const float4 *>(p.Yd + base + i));
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < kDrainUnroll; q++) {
-            const int i = idx + q * S;
-            if (i >= wv) break;
-            const unsigned a = acc32 + (unsigned)i * 4u;
-            // the common case: nothing in the quad can enter the result (an untouched slot holds -0.0f and is
-            // rejected like any small dot product once lo > 0)
-            if (filter && quad_rejected<KIND>(p, fr, lo, lc, la, x[q], yt[q], yc[q], yd[q])) {
-                sts128(a, sent4);
-                continue;
-            }
-            if (!drain_quad_slow<KIND>(p, fr, filter, lo, a, base + i, x[q], yt[q], yc[q], yd[q], cand, s_cnt)) {
-                *s_overflow = 1;
-                return i;  // resume at this quad
+    const int n_iter = (width + S - 1) / S;
+
+    // ---- phase 1: coarse test against the per-block minima; lane i of the warp holds the block of step i (yv) ----
+    const bool coarse = filter && (KIND == KIND_C || KIND == KIND_D) && p.y_block_min != nullptr && lo > 0.f && lc >= 0.f;
+    if (coarse) {  // block-uniform
+        for (int it = 0; it < n_iter; it++) {
+            const float bound = fmaf(lc, __shfl_sync(0xffffffffu, yv, it), la);
+            const int i = tid * 4 + it * S;
+            if ((todo >> it & 1u) && i < wv) {
+                const unsigned a = acc32 + (unsigned)i * 4u;
+                const float4 x = lds128(a);
+                if ((x.x < bound) & (x.y < bound) & (x.z < bound) & (x.w < bound)) {
+                    sts128(a, sent4);
+                    todo &= ~(1u << it);
+                }
             }
         }
     }
-    // the last, partial quad of the matrix (n_cols % 4 slots of the last panel): one thread, scalar Y loads
-    if (wv < width && idx != kDrainDone && ((wv >> 2) % NT) == (int)threadIdx.x) {
-        const unsigned a = acc32 + (unsigned)wv * 4u;
-        const float4 x = lds128(a);
-        float4 yt = sent4, yc = sent4, yd = sent4;
-        if (useT) yt = load_y4(p.Yt, base + wv, p.n_cols);
-        if (useC) yc = load_y4(p.Yc, base + wv, p.n_cols);
-        if (useD) yd = load_y4(p.Yd, base + wv, p.n_cols);
-        if (!drain_quad_slow<KIND>(p, fr, filter, lo, a, base + wv, x, yt, yc, yd, cand, s_cnt)) {
-            *s_overflow = 1;
-            return wv;
+
+    // ---- phase 2: the per-slot test on what is left ----
+    while (todo) {
+        int its[B];
+        float4 x[B], yt[B], yc[B], yd[B];
+        unsigned rest = todo;
+#pragma unroll
+        for (int b = 0; b < B; b++) {
+            its[b] = -1;
+            yt[b] = sent4; yc[b] = sent4; yd[b] = sent4;
+            if (rest) {
+                const int it = __ffs(rest) - 1;
+                rest &= rest - 1u;
+                its[b] = it;
+                const int i = tid * 4 + it * S;
+                x[b] = lds128(acc32 + (unsigned)i * 4u);
+                if (i < wv) {
+                    if (useT) yt[b] = __ldg(reinterpret_cast<const float4 *>(p.Yt + base + i));
+                    if (useC) yc[b] = __ldg(reinterpret_cast<const float4 *>(p.Yc + base + i));
+                    if (useD) yd[b] = __ldg(reinterpret_cast<const float4 *>(p.Yd + base + i));
+                } else {  // the last, partial quad of the matrix
+                    if (useT) yt[b] = load_y4(p.Yt, base + i, p.n_cols);
+                    if (useC) yc[b] = load_y4(p.Yc, base + i, p.n_cols);
+                    if (useD) yd[b] = load_y4(p.Yd, base + i, p.n_cols);
+                }
+            }
         }
-        return kDrainDone;
+#pragma unroll
+        for (int b = 0; b < B; b++) {
+            if (its[b] >= 0) {
+                const int i = tid * 4 + its[b] * S;
+                const unsigned a = acc32 + (unsigned)i * 4u;
+                const unsigned m = survivor_mask<KIND>(p, fr, filter, lo, lc, la, x[b], yt[b], yc[b], yd[b]);
+                if (m == 0u) sts128(a, sent4);
+                else if (!push_quad(p.cap, a, base + i, x[b], m, cand, s_cnt)) {
+                    *s_overflow = 1;
+                    return todo;  // this quad and everything after it
+                }
+                todo &= ~(1u << its[b]);
+            }
+        }
     }
-    return idx;
+    return 0u;
 }
 
 // Same for MODE_MATRIX target columns (s_plus.h:175-188): only the columns listed in the target row's sorted
@@ -566,8 +585,11 @@ __device__ __forceinline__ void drain_pass_list(const KnnDev &p, float *acc, int
         if (q > tlo && __ldg(p.t_indices + q - 1) == col) continue;  // one owner per column
         const float xy = acc[col - base];
         if (__float_as_uint(xy) == kSentinelBits) continue;
-        if (push_raw(cand, s_cnt, p.cap, xy, col)) acc[col - base] = __uint_as_float(kSentinelBits);
-        else overflow = true;
+        int pos = p.cap;
+        if (*reinterpret_cast<volatile int *>(s_cnt) < p.cap) pos = atomicAdd(s_cnt, 1);
+        if (pos >= p.cap) { overflow = true; continue; }  // the slot keeps its value for the next pass
+        cand[pos] = make_raw(xy, col);
+        acc[col - base] = __uint_as_float(kSentinelBits);
     }
     if (overflow) *s_overflow = 1;
 }
@@ -756,7 +778,7 @@ knn_flat_kernel(const __grid_constant__ KnnDev p) {
 
     for (int i = tid * 4; i < p.W; i += NT * 4) *reinterpret_cast<float4 *>(acc + i) = sentinel4;
 #if SPY_PHASE_TIMING
-    long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long ph[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     long long t_last = clock64();
     __shared__ unsigned long long s_busy;
     if (tid == 0) s_busy = 0ull;
@@ -846,6 +868,7 @@ knn_flat_kernel(const __grid_constant__ KnnDev p) {
             SPY_TICK(1);
             if (pn == p.n_panels - 1) load_next_entries();  // in flight during the last drain + final selection
             if (!landed) continue;
+            SPY_TICK(13);
             FastRow fr;
             fr.A0 = p.stab + p.l1 * p.t1 * sr.Xt;
             fr.cT = p.l1 * p.t2;
@@ -869,19 +892,35 @@ knn_flat_kernel(const __grid_constant__ KnnDev p) {
                 tlo = lower_bound_dev(p.t_indices, ts, te, base);
                 thi = lower_bound_dev(p.t_indices, tlo, te, base + width);
             }
-            int resume = tid * 4;
+            // steps of this panel the thread still has to drain: bit it <=> quad tid + it * NT exists
+            unsigned todo = 0u;
+            for (int it = 0; tid * 4 + it * NT * 4 < width; it++) todo |= 1u << it;
+            // per-block minimum of Y for the coarse test: lane i of a warp holds the block of the warp's step i
+            float yv = 0.f;
+            if (p.y_block_min != nullptr && (tid & 31) * NT * 4 < width) {
+                const int blk = ((base + (tid & ~31) * 4) >> 7) + (tid & 31) * (NT * 4 >> 7);
+                if (blk < ((p.n_cols + 127) >> 7)) yv = __ldg(p.y_block_min + blk);
+            }
             for (;;) {
                 if (p.target_mode == SPY_SEL_MATRIX) drain_pass_list<NT>(p, acc, base, tlo, thi, cand, &s_cnt, &s_overflow);
-                else resume = drain_pass<NT, KIND>(p, fr, acc32, base, width, lo, cand, &s_cnt, &s_overflow, resume);
+                else todo = drain_pass<NT, KIND>(p, fr, acc32, base, width, lo, yv, cand, &s_cnt, &s_overflow, todo);
+#if SPY_PHASE_TIMING
+                if (tid == 0) { const long long _t = clock64(); ph[pn == 0 ? 11 : 12] += _t - t_last; t_last = _t; }
+#endif
                 __syncthreads();
-                SPY_TICK(3);
+                SPY_TICK(pn == 0 ? 3 : 8);
+#if SPY_PHASE_TIMING
+                if (tid == 0) ph[pn == 0 ? 9 : 10] += 1;
+#endif
                 const bool again = s_overflow != 0;
                 const int cnt = min(s_cnt, p.cap);
                 // exact values of the raw candidates, all lanes busy (computeSimilarity, s_plus.h:129-156, 206)
                 for (int i = n_eval + tid; i < cnt; i += NT) {
                     const u64 raw = cand[i];
                     const int col = (int)(unsigned)(raw & 0xffffffffull);
-                    const float val = similarity_value(p, sr, col, __uint_as_float((unsigned)(raw >> 32)));
+                    const float val = similarity_value(p, sr, __uint_as_float((unsigned)(raw >> 32)),
+                                                       p.l1 != 0.f ? __ldg(p.Yt + col) : 0.f, p.l2 != 0.f ? __ldg(p.Yc + col) : 0.f,
+                                                       p.l3 != 0.f ? __ldg(p.Yd + col) : 0.f);
                     u64 key = 0ull;
                     if (val >= p.thr) key = make_key(val, col);
                     cand[i] = (key > tau) ? key : 0ull;
@@ -929,7 +968,7 @@ knn_flat_kernel(const __grid_constant__ KnnDev p) {
     __syncthreads();
     if (tid == 0) {
         ph[2] = (long long)(s_busy / (NT / 32));  // mean over warps of "cycles from the end of staging to the warp's own end"
-        for (int i = 0; i < 8; i++) atomicAdd(p.phase + i, (u64)ph[i]);
+        for (int i = 0; i < 16; i++) atomicAdd(p.phase + i, (u64)ph[i]);
     }
 #endif
 }
