@@ -283,9 +283,13 @@ def validate_inputs(matrix1, matrix2, weight_depop_matrix1, weight_depop_matrix2
     for name, cols in (("filter_cols", filter_cols), ("target_cols", target_cols)):
         if cols is None:
             continue
-        if not (sp.issparse(cols) or isinstance(cols, (list, np.ndarray))):
+        if not (_is_matrix(cols) or isinstance(cols, (list, np.ndarray))):
             raise TypeError(f"{name} must be a sparse matrix, list, numpy array, or None")
-        if sp.issparse(cols) and cols.data.shape[0] != 0:
+        if isinstance(cols, DeviceMatrix):
+            if cols.nnz != 0 and cols.shape != (matrix1.shape[0], matrix2.shape[1]):
+                raise ValueError(f"{name} shape {cols.shape} does not match expected shape "
+                                 f"{(matrix1.shape[0], matrix2.shape[1])}")
+        elif sp.issparse(cols) and cols.data.shape[0] != 0:
             expected = (matrix1.shape[0], matrix2.shape[1])
             if cols.shape != expected:
                 raise ValueError(f"{name} shape {cols.shape} does not match expected shape {expected}")
@@ -296,7 +300,9 @@ def validate_inputs(matrix1, matrix2, weight_depop_matrix1, weight_depop_matrix2
 
 
 def selector_mode(cols) -> int:
-    """s_plus_utils.pyx:311-361."""
+    """s_plus_utils.pyx:311-361 (a DeviceMatrix is a sparse matrix that already lives in HBM)."""
+    if isinstance(cols, DeviceMatrix):
+        return MODE_MATRIX if cols.nnz != 0 else MODE_NONE
     if sp.issparse(cols) and cols.data.shape[0] != 0:
         return MODE_MATRIX
     if isinstance(cols, (list, np.ndarray)) and len(cols) != 0:
@@ -410,7 +416,14 @@ class KnnJob:
         self.filter_mode = selector_mode(filter_cols)
         self.target_mode = selector_mode(target_cols)
         for which, cols, mode in (("filter_m", filter_cols, self.filter_mode), ("target_m", target_cols, self.target_mode)):
-            if mode == MODE_MATRIX:  # per-row lists, sorted for the in-kernel range search
+            if mode == MODE_MATRIX and isinstance(cols, DeviceMatrix):  # already in HBM: rows sorted on the device
+                m = transpose_csr(ctx, cols.stored) if cols.transposed else cols.stored
+                m = filter_csr(ctx, m, drop_zeros=True)
+                if not m.sorted_rows:
+                    m = DeviceCSR(m.n_rows, m.n_cols, m.indptr, m.indices.clone(), m.data.clone(), sorted_rows=False)
+                    _lib.check(ctx.lib.spy_csr_sort_rows_dev(m.n_rows, _ptr(m.indptr), _ptr(m.indices), _ptr(m.data), ctx.sptr))
+                setattr(self, which, (m.indptr, m.indices))
+            elif mode == MODE_MATRIX:  # per-row lists, sorted for the in-kernel range search
                 c = cols.tocsr()
                 c.eliminate_zeros()
                 c.sort_indices()

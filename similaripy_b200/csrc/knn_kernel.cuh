@@ -669,13 +669,19 @@ struct NextFirst {
 
 template <int NT, int G>
 __device__ __forceinline__ bool accumulate_chunk(const ExpandArgs x, int n, const int *st_u, const float *st_v,
-                                                 unsigned accb32, const NextFirst pre, bool want_next, NextFirst &nxt) {
+                                                 unsigned accb32, const NextFirst pre, bool want_next, NextFirst &nxt,
+                                                 int *next_entry) {
     constexpr int GROUPS = NT / G;
+    constexpr int GPW = 32 / G;        // groups per warp
     constexpr int U = unroll_for(NT);  // 16-byte loads (2 pairs each) in flight per lane
     const int tid = threadIdx.x;
     const int gl = tid & (G - 1);
-    const int grp0 = (tid & ~31) / G;  // first group of this warp: the loop below is warp-uniform
-    int idx = tid / G;
+    const int gw = (tid & 31) / G;     // the group's position inside its warp
+    // A warp's first two batches of GPW entries are fixed (warp w: entries w * GPW + {0, GROUPS}); further batches are
+    // claimed from a shared counter two passes ahead -- the expansion's `schedule(dynamic)` inside the CTA: warps
+    // whose gathers came back late do fewer passes, so the panel barrier waits for less.
+    int base0 = (tid & ~31) / G, base1 = base0 + GROUPS, base2;
+    int idx = base0 + gw;
     bool any = false;
     // software pipeline over the group's entries: the bounds of entry i + 2 are being fetched and the pairs of
     // entry i + 1 are on their way into L2 while the pairs of entry i are gathered and accumulated
@@ -699,13 +705,18 @@ __device__ __forceinline__ bool accumulate_chunk(const ExpandArgs x, int n, cons
     };
     if (pre.valid) { s = pre.s; e = pre.e; }
     else fetch(idx, s, e);
-    fetch(idx + GROUPS, s1, e1);
+    fetch(base1 + gw, s1, e1);
     int e_far = 0;  // end of the first entry's segment in the next panel (its begin is this panel's end)
     if (want_next && idx < n) e_far = __ldg(x.b_split + (size_t)st_u[idx] * x.split_stride + x.pn + 2);
     nxt.s = e; nxt.valid = want_next;
     bool first_pass = true;
-    for (int i0 = grp0; i0 < n; i0 += GROUPS) {
-        fetch(idx + 2 * GROUPS, s2, e2);
+    while (base0 < n) {  // warp-uniform
+        base2 = n;
+        if (base1 < n) {  // claim the batch of the pass after next
+            if ((tid & 31) == 0) base2 = atomicAdd(next_entry, GPW);
+            base2 = __shfl_sync(0xffffffffu, base2, 0);
+        }
+        fetch(base2 + gw, s2, e2);
         if (!first_pass) prefetch_l2(s1, e1);  // its bounds were fetched a whole pass ago
         const float v = (idx < n) ? st_v[idx] : 0.f;
         const int sa = s & ~1;  // pairs are 8 bytes: an even position is 16-byte aligned
@@ -734,7 +745,8 @@ __device__ __forceinline__ bool accumulate_chunk(const ExpandArgs x, int n, cons
         }
         if (first_pass) { prefetch_l2(s1, e1); first_pass = false; }
         s = s1; e = e1; s1 = s2; e1 = e2;
-        idx += GROUPS;
+        base0 = base1; base1 = base2;
+        idx = base0 + gw;
     }
     nxt.e = e_far;
     if (want_next) prefetch_l2(nxt.s, nxt.e);
@@ -768,6 +780,7 @@ knn_flat_kernel(const __grid_constant__ KnnDev p) {
     constexpr int kTmpCap = CH;
 
     __shared__ int s_cnt, s_overflow, s_live;
+    __shared__ int s_entry[2];  // next unclaimed entry of the staged chunk (alternating between accumulate calls)
     __shared__ int s_next[5];  // the NEXT row of this CTA: queue slot, output position, row id, A-row begin / end
     __shared__ u64 s_tau, s_pivot;
 
@@ -807,9 +820,10 @@ knn_flat_kernel(const __grid_constant__ KnnDev p) {
             if (tid < e - b) { u_n = __ldg(p.a_indices + b + tid); v_n = __ldg(p.a_data + b + tid); }
         }
     };
-    if (tid == 0) claim_next();
+    if (tid == 0) { claim_next(); s_entry[0] = 2 * (NT / G); s_entry[1] = 2 * (NT / G); }
     __syncthreads();
     load_next_entries();
+    int calls = 0;  // accumulate_chunk calls so far: call c claims from s_entry[c & 1] and re-arms the other counter
 
     for (;;) {
         const int slot = s_next[0];
@@ -855,8 +869,10 @@ knn_flat_kernel(const __grid_constant__ KnnDev p) {
                 const ExpandArgs x = {p.b_indptr, p.b_split, p.b_pairs, p.split_stride, p.n_panels, pn};
                 const bool first = c0 == a0;  // the cross-panel prefetch covers the first chunk of the row
                 NextFirst none = {0, 0, false}, got = none;
+                if (tid == 0) s_entry[(calls + 1) & 1] = 2 * (NT / G);  // last used by call `calls - 1`: two barriers ago
                 any |= accumulate_chunk<NT, G>(x, n, st_u, st_v, accb32, first ? pre : none,
-                                               first && pn + 1 < p.n_panels, got);
+                                               first && pn + 1 < p.n_panels, got, &s_entry[calls & 1]);
+                calls++;
                 if (first) pre = got;
             }
             if (pn == 0 && tid == 0) claim_next();  // hidden behind the other warps' accumulation

@@ -234,3 +234,54 @@ def test_properties_at_scale():
     # (6) spot rows against the oracle
     ref = oracle.similarity("cosine", m, k=k, target_rows=sub, format_output="csr")
     assert_topk_parity(ref, b, k=k, rtol=1e-5, what="scale spot rows")
+
+
+# ---- dense candidate sets: buffer overflow, sampling rounds, coarse block-minimum filter, several panels -----------
+_DENSE = None
+
+
+def _dense_urm():
+    """3000 users x 20003 items, 2 % dense: an item row of URM.T expands to ~24k products over ~14k distinct columns,
+    far more than the 2048-entry candidate buffer (n_cols deliberately not a multiple of 4)."""
+    global _DENSE
+    if _DENSE is None:
+        rng = np.random.default_rng(77)
+        _DENSE = sp.random_array((3000, 20003), density=0.02, format="csr", dtype=np.float32, random_state=rng)
+    return _DENSE
+
+
+@pytest.mark.parametrize("name,kw", PRESETS + [("cosine", dict(shrink=5.0, shrink_type="bayesian")),
+                                                ("tversky", dict(alpha=0.3, beta=0.9, shrink=2.0))],
+                         ids=[p[0] for p in PRESETS] + ["cosine_bayes", "tversky_shrink"])
+@pytest.mark.parametrize("tuning", [None, dict(panel_width=4096), dict(threads=512, panel_width=2048, group=16)],
+                         ids=["plan", "panels5", "t512g16"])
+def test_dense_candidates_overflow_paths(name, kw, tuning):
+    urm = _dense_urm()
+    a = urm.T.tocsr()
+    rows = np.arange(0, a.shape[0], 97, dtype=np.int32)  # 207 target rows
+    k = 100
+    got = getattr(sim, name)(a, urm, k=k, target_rows=rows, verbose=False, format_output="csr", tuning=tuning, **kw)
+    ref = oracle.similarity(name, a, urm, k=k, target_rows=rows, verbose=False, format_output="csr", **kw)
+    stats = assert_topk_parity(ref, got, k=k, rtol=1e-5, what=f"dense {name} {tuning}")
+    assert stats["full_rows"] >= 200
+
+
+@pytest.mark.parametrize("k", [1, 7, 700, 3000])
+def test_dense_candidates_k_extremes(k):
+    urm = _dense_urm()
+    a = urm.T.tocsr()
+    rows = np.arange(5, a.shape[0], 401, dtype=np.int32)
+    got = sim.cosine(a, urm, k=k, target_rows=rows, verbose=False, format_output="csr")
+    ref = oracle.similarity("cosine", a, urm, k=k, target_rows=rows, verbose=False, format_output="csr")
+    assert_topk_parity(ref, got, k=k, rtol=1e-5, what=f"dense k={k}")
+
+
+def test_dense_candidates_binary_integer_exact():
+    """Integer-valued data: dot products are order independent, so the values must be bit-exact."""
+    urm = _dense_urm().copy()
+    urm.data = np.floor(urm.data * 4).astype(np.float32) + 1.0
+    a = urm.T.tocsr()
+    rows = np.arange(3, a.shape[0], 211, dtype=np.int32)
+    got = sim.dot_product(a, urm, k=150, target_rows=rows, verbose=False, format_output="csr", tuning=dict(panel_width=8192))
+    ref = oracle.similarity("dot_product", a, urm, k=150, target_rows=rows, verbose=False, format_output="csr")
+    assert_topk_parity(ref, got, k=150, rtol=0.0, what="dense integer dot")
