@@ -114,14 +114,15 @@ static int make_plan(const spy_knn_args &a, int device, Plan &pl) {
     if (stride <= 8) stride = next_pow2(stride);  // one 32-byte sector per B row
     pl.split_stride = (pl.n_panels > 1) ? stride : 0;
     pl.smem_bytes = (size_t)W * 4 + fixed;
-    // lanes per B-row segment: a group has unroll_for(threads) 16-byte loads (2 pairs each) per lane in flight before its
-    // first add, so 2 * G * unroll_for(threads) should just cover the mean segment (entries of a B row inside one panel)
+    // lanes per B-row segment: a batch is 2 * G * unroll pairs (16-byte gathers of 2 pairs, `unroll` per lane before
+    // the first add); measured best when a batch covers about two thirds of the mean segment (entries of a B row
+    // inside one panel), so that a typical segment takes two nearly full batches
     int G = a.group;
     if (G == 0) {
         G = 8;
         if (a.b_nnz > 0 && a.b_rows > 0) {
             const double seg = (double)a.b_nnz / ((double)a.b_rows * pl.n_panels);
-            const double want = seg * 1.25 / (2 * unroll_for(pl.threads));
+            const double want = seg * 0.65 / (2 * unroll_for(pl.threads));
             G = want <= 5.7 ? 4 : want <= 11.4 ? 8 : want <= 22.7 ? 16 : 32;
         }
     }

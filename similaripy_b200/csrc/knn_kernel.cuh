@@ -382,10 +382,12 @@ __device__ __forceinline__ void smem_add_f32(unsigned addr, float x) {
     asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(addr), "f"(x) : "memory");
 }
 
-// 16-byte gathers (two pairs each) a lane has in flight before its first add; 64 registers per thread
-// (1024 resident threads per SM: one CTA of 1024 or two of 512) leave room for 4
+// 16-byte gathers (two pairs each) a lane issues before its first add.  Measured on cfg2 (B200, 50-entry segments,
+// 8 lanes per segment): 2 -> 204 ms, 1 -> 209 ms, 4 -> 220 ms, 3 -> 225 ms: with 64 registers per thread the deeper
+// batches cost more in register pressure than they gain in memory-level parallelism (the L2 prefetch of the next
+// segment provides that).
 #ifndef SPY_UNROLL
-#define SPY_UNROLL 4
+#define SPY_UNROLL 2
 #endif
 __host__ __device__ constexpr int unroll_for(int threads) { return SPY_UNROLL; }
 // Entries of a target row staged in shared memory at a time (8 bytes each): a quarter more than the CTA has
