@@ -465,7 +465,8 @@ __device__ __forceinline__ u64 make_raw(float xy, int col) { return ((u64)__floa
 // afterwards for the whole buffer with all lanes busy (the IEEE division of computeSimilarity would otherwise run
 // with one or two lanes of a warp active).  A survivor that does not fit keeps its slot value.  Returns false
 // when the buffer was full.
-__device__ __forceinline__ bool push_quad(int cap, unsigned a, int col0, const float4 &x, unsigned m, u64 *cand, int *s_cnt) {
+__device__ __forceinline__ bool push_quad(int cap, unsigned a, int col0, const float4 &x, unsigned m, u64 *cand, int *s_cnt,
+                                          bool keep_rejected) {
     const float sent = __uint_as_float(kSentinelBits);
     const float xs[4] = {x.x, x.y, x.z, x.w};
     const int cnt = __popc(m);
@@ -473,11 +474,12 @@ __device__ __forceinline__ bool push_quad(int cap, unsigned a, int col0, const f
     if (*reinterpret_cast<volatile int *>(s_cnt) < cap) pos = atomicAdd(s_cnt, cnt);  // few lanes: they serialise on s_cnt
     const int fit = max(0, min(cnt, cap - pos));
     float ws[4] = {sent, sent, sent, sent};
+    if (keep_rejected) { ws[0] = xs[0]; ws[1] = xs[1]; ws[2] = xs[2]; ws[3] = xs[3]; }  // only buffered slots are reset
 #pragma unroll
     for (int r = 0; r < 4; r++)
         if (m & (1u << r)) {
             const int w = __popc(m & ((1u << r) - 1u));
-            if (w < fit) cand[pos + w] = make_raw(xs[r], col0 + r);
+            if (w < fit) { cand[pos + w] = make_raw(xs[r], col0 + r); ws[r] = sent; }
             else ws[r] = xs[r];
         }
     sts128(a, make_float4(ws[0], ws[1], ws[2], ws[3]));
@@ -497,7 +499,8 @@ __device__ __forceinline__ bool push_quad(int cap, unsigned a, int col0, const f
 // again -- else 0.  No block barriers inside.
 template <int NT, int KIND>
 __device__ __forceinline__ unsigned drain_pass(const KnnDev &p, const FastRow &fr, unsigned acc32, int base, int width, float lo,
-                                               float yv, u64 *cand, int *s_cnt, int *s_overflow, unsigned todo) {
+                                               float yv, u64 *cand, int *s_cnt, int *s_overflow, unsigned todo,
+                                               bool keep_rejected) {
     const float sent = __uint_as_float(kSentinelBits);
     const float4 sent4 = make_float4(sent, sent, sent, sent);
     constexpr int S = NT * 4;
@@ -525,7 +528,7 @@ __device__ __forceinline__ unsigned drain_pass(const KnnDev &p, const FastRow &f
                 const unsigned a = acc32 + (unsigned)i * 4u;
                 const float4 x = lds128(a);
                 if ((x.x < bound) & (x.y < bound) & (x.z < bound) & (x.w < bound)) {
-                    sts128(a, sent4);
+                    if (!keep_rejected) sts128(a, sent4);
                     todo &= ~(1u << it);
                 }
             }
@@ -564,8 +567,9 @@ __device__ __forceinline__ unsigned drain_pass(const KnnDev &p, const FastRow &f
                 const int i = tid * 4 + its[b] * S;
                 const unsigned a = acc32 + (unsigned)i * 4u;
                 const unsigned m = survivor_mask<KIND>(p, fr, filter, lo, lc, la, x[b], yt[b], yc[b], yd[b]);
-                if (m == 0u) sts128(a, sent4);
-                else if (!push_quad(p.cap, a, base + i, x[b], m, cand, s_cnt)) {
+                if (m == 0u) {
+                    if (!keep_rejected) sts128(a, sent4);
+                } else if (!push_quad(p.cap, a, base + i, x[b], m, cand, s_cnt, keep_rejected)) {
                     *s_overflow = 1;
                     return todo;  // this quad and everything after it
                 }
@@ -614,6 +618,9 @@ struct ExpandArgs {  // what the expansion needs of KnnDev, by value: the routin
 #define SPY_TICK(id) do { if (tid == 0) { const long long _t = clock64(); ph[id] += _t - t_last; t_last = _t; } } while (0)
 #else
 #define SPY_TICK(id) do { } while (0)
+#endif
+#ifndef SPY_SPECULATE
+#define SPY_SPECULATE 1
 #endif
 #ifndef SPY_PREFETCH
 #define SPY_PREFETCH 1
@@ -919,20 +926,9 @@ knn_flat_kernel(const __grid_constant__ KnnDev p) {
                 const int blk = ((base + (tid & ~31) * 4) >> 7) + (tid & 31) * (NT * 4 >> 7);
                 if (blk < ((p.n_cols + 127) >> 7)) yv = __ldg(p.y_block_min + blk);
             }
-            for (;;) {
-                if (p.target_mode == SPY_SEL_MATRIX) drain_pass_list<NT>(p, acc, base, tlo, thi, cand, &s_cnt, &s_overflow);
-                else todo = drain_pass<NT, KIND>(p, fr, acc32, base, width, lo, yv, cand, &s_cnt, &s_overflow, todo);
-#if SPY_PHASE_TIMING
-                if (tid == 0) { const long long _t = clock64(); ph[pn == 0 ? 11 : 12] += _t - t_last; t_last = _t; }
-#endif
-                __syncthreads();
-                SPY_TICK(pn == 0 ? 3 : 8);
-#if SPY_PHASE_TIMING
-                if (tid == 0) ph[pn == 0 ? 9 : 10] += 1;
-#endif
-                const bool again = s_overflow != 0;
-                const int cnt = min(s_cnt, p.cap);
-                // exact values of the raw candidates, all lanes busy (computeSimilarity, s_plus.h:129-156, 206)
+            // exact values of the raw candidates cand[n_eval, cnt), all lanes busy (computeSimilarity, s_plus.h:129-156, 206);
+            // a candidate that cannot beat the valid running bound tau dies here
+            auto evaluate = [&](int cnt) {
                 for (int i = n_eval + tid; i < cnt; i += NT) {
                     const u64 raw = cand[i];
                     const int col = (int)(unsigned)(raw & 0xffffffffull);
@@ -944,21 +940,131 @@ knn_flat_kernel(const __grid_constant__ KnnDev p) {
                     cand[i] = (key > tau) ? key : 0ull;
                 }
                 n_eval = cnt;
-                __syncthreads();
-                SPY_TICK(4);
-                if (again || cnt > p.cap / 2) {  // tighten tau while the buffer is reasonably full
-                    if (tid == 0) s_overflow = 0;
-                    tighten_topk<NT>(cand, cnt, p.k, tmp, kTmpCap, &s_cnt, &s_tau, &s_live, &s_pivot);
-                    staged_c0 = -1;  // tmp overlays the staged row
-                    tau = s_tau;
-                    lo = reject_bound(p, tau);
-                    n_eval = s_cnt;
-                    SPY_TICK(5);
+            };
+
+            // ---- speculative bound for a row that has none yet (its first non-empty panel) ----
+            // Without a bound the first pass floods the buffer and two selections are needed before the pre-filter
+            // bites.  Instead: SAMPLE the panel (one quad per thread, spread over all blocks, slots left untouched),
+            // take the r-th best sample as the bound, r chosen so that the panel holds k candidates above it with
+            // overwhelming probability, and drain with it while KEEPING rejected slots.  The bound is then
+            // validated -- at least k buffered candidates beat it -- before the panel is cleared; if it is not,
+            // the panel is drained again with the valid bound, so results never depend on the sample.
+            u64 tau_s = 0ull;
+            bool spec = false;
+            {
+                const int n_iter = (width + NT * 4 - 1) / (NT * 4);
+                // (n_eval == 0: nothing buffered yet -- a register every thread agrees on; s_cnt itself is modified below)
+                if (SPY_SPECULATE && tau == 0ull && !p.exact_only && p.target_mode != SPY_SEL_MATRIX && n_iter >= 4 && n_eval == 0) {
+                    const int i = tid * 4 + (tid % n_iter) * NT * 4;
+                    float4 x = sentinel4;
+                    if (i + 3 < width) x = lds128(acc32 + (unsigned)i * 4u);
+                    const float xs[4] = {x.x, x.y, x.z, x.w};
+                    unsigned m = 0u;
+#pragma unroll
+                    for (int r = 0; r < 4; r++)
+                        if (__float_as_uint(xs[r]) != kSentinelBits) m |= 1u << r;
+                    // one reservation per warp: inclusive scan of the lanes' counts
+                    const int c = __popc(m);
+                    int inc = c;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int v = __shfl_up_sync(0xffffffffu, inc, o);
+                        if ((tid & 31) >= o) inc += v;
+                    }
+                    int wbase = 0;
+                    if ((tid & 31) == 31 && inc > 0) wbase = atomicAdd(&s_cnt, inc);
+                    wbase = __shfl_sync(0xffffffffu, wbase, 31);
+                    int pos = wbase + inc - c;
+#pragma unroll
+                    for (int r = 0; r < 4; r++)
+                        if ((m & (1u << r)) && pos < p.cap) cand[pos++] = make_raw(xs[r], base + i + r);
+                        else if (m & (1u << r)) pos++;
+                    __syncthreads();
+                    const int attempts = s_cnt, n_s = min(attempts, p.cap);
+                    evaluate(n_s);
+                    __syncthreads();
+                    const float f = (float)min(width, NT * 4) / (float)width * (float)n_s / (float)max(attempts, 1);
+                    const float kf = (float)p.k * f;
+#ifdef SPY_SPEC_FORCE_RANK  // test builds: a bound that is almost never valid, to exercise the re-drain path
+                    const int r_s = SPY_SPEC_FORCE_RANK;
+#else
+                    const int r_s = (int)ceilf(kf + 3.5f * sqrtf(kf) + 1.5f);
+#endif
+                    if (f < 0.4f && n_s >= 8 * r_s) {  // uniform
+                        select_topk<NT>(cand, n_s, r_s, tmp, kTmpCap, &s_cnt, &s_tau, &s_live, &s_pivot);
+                        staged_c0 = -1;  // tmp overlays the staged row
+                        if (s_cnt == r_s) { tau_s = s_tau; spec = true; }
+                    }
+                    __syncthreads();
+                    if (tid == 0) { s_cnt = 0; s_tau = 0ull; }  // the sample was only read: its slots are all still there
+                    n_eval = 0;
+                    __syncthreads();
                 }
-                if (!again) break;
+            }
+
+            for (int attempt = 0; attempt < 2; attempt++) {
+                const float lo_use = spec ? reject_bound(p, tau_s > tau ? tau_s : tau) : lo;
+                for (;;) {
+                    if (p.target_mode == SPY_SEL_MATRIX) drain_pass_list<NT>(p, acc, base, tlo, thi, cand, &s_cnt, &s_overflow);
+                    else todo = drain_pass<NT, KIND>(p, fr, acc32, base, width, spec ? fmaxf(lo_use, lo) : lo, yv, cand, &s_cnt,
+                                                     &s_overflow, todo, spec);
+#if SPY_PHASE_TIMING
+                    if (tid == 0) { const long long _t = clock64(); ph[pn == 0 ? 11 : 12] += _t - t_last; t_last = _t; }
+#endif
+                    __syncthreads();
+                    SPY_TICK(pn == 0 ? 3 : 8);
+#if SPY_PHASE_TIMING
+                    if (tid == 0) ph[pn == 0 ? 9 : 10] += 1;
+#endif
+                    const bool again = s_overflow != 0;
+                    const int cnt = min(s_cnt, p.cap);
+                    evaluate(cnt);
+                    __syncthreads();
+                    SPY_TICK(4);
+                    if (again || cnt > p.cap / 2) {  // tighten tau while the buffer is reasonably full
+                        if (tid == 0) s_overflow = 0;
+                        tighten_topk<NT>(cand, cnt, p.k, tmp, kTmpCap, &s_cnt, &s_tau, &s_live, &s_pivot);
+                        staged_c0 = -1;  // tmp overlays the staged row
+                        tau = s_tau;
+                        lo = reject_bound(p, tau);
+                        n_eval = s_cnt;
+                        SPY_TICK(5);
+                    }
+                    if (!again) break;
+                }
+                if (!spec) break;
+                // validate the speculative bound: do k buffered candidates beat it?
+                if (tid == 0) s_live = 0;
+                __syncthreads();
+                int above = 0;
+                for (int i = tid; i < n_eval; i += NT) above += cand[i] > tau_s ? 1 : 0;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) above += __shfl_xor_sync(0xffffffffu, above, o);
+                if ((tid & 31) == 0 && above) atomicAdd(&s_live, above);
+                __syncthreads();
+                const bool valid = s_live >= p.k;
+                __syncthreads();
+                spec = false;
+                if (valid) {
+                    if (tau_s > tau) { tau = tau_s; lo = reject_bound(p, tau); }
+                    for (int i = tid * 4; i < width; i += NT * 4) sts128(acc32 + (unsigned)i * 4u, sentinel4);  // clear the panel
+                    __syncthreads();  // before anyone accumulates the next panel into it
+                    if (n_eval > 2 * p.k) {  // sharpen the bound for the panels to come (one sampling round)
+                        tighten_topk<NT>(cand, n_eval, p.k, tmp, kTmpCap, &s_cnt, &s_tau, &s_live, &s_pivot);
+                        staged_c0 = -1;
+                        tau = s_tau;
+                        lo = reject_bound(p, tau);
+                        n_eval = s_cnt;
+                    }
+                    break;
+                }
+                // not validated: everything rejected so far is still in the panel; drain it again with the valid bound
+                todo = 0u;
+                for (int it = 0; tid * 4 + it * NT * 4 < width; it++) todo |= 1u << it;
             }
             if (p.target_mode == SPY_SEL_MATRIX) {  // touched slots outside the target list
                 for (int i = tid * 4; i < width; i += NT * 4) *reinterpret_cast<float4 *>(acc + i) = sentinel4;
+                __syncthreads();  // before anyone accumulates the next panel into it
             }
         }
 

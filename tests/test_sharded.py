@@ -189,3 +189,19 @@ def test_gpu_sharded_gather_single_process_group():
                 assert got.data.shape[0] == rows.shape[0] * 15  # the reference's COO keeps every slab entry
     finally:
         dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_two_gpus_nccl_gather():
+    """The real N>1 path: torchrun with one rank per GPU, NCCL all-gather over NVLink (needs >= 2 visible GPUs)."""
+    import subprocess
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    world = 2
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), os.path.join(HERE, "sharded_worker.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert out.stdout.count("SHARDED_OK") == world
