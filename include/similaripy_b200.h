@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SPY_ABI_VERSION 3
+#define SPY_ABI_VERSION 4
 
 typedef enum {
     SPY_OK = 0,
@@ -183,13 +183,14 @@ int spy_csr_col_count_dev(int64_t nnz, const int32_t *indices, int32_t n_cols, i
 int64_t spy_scan_tmp_bytes(int64_t n);
 int spy_exclusive_scan_i32_dev(int64_t n, const int32_t *counts, int32_t *offsets, void *tmp, void *stream);
 int spy_exclusive_scan_i64_dev(int64_t n, const int32_t *counts, int64_t *offsets, void *tmp, void *stream);
-/* CSR -> CSC (== transpose in CSR) with ascending indices in every output row.
- * Replaces scipy's csr_tocsc behind matrix1.T.tocsr() (s_plus.pyx:170,205-206).
- * t_indptr must already hold the exclusive scan of the column counts (n_cols+1);
- * cursor is n_cols int32 of scratch. */
+/* CSR -> CSC (== transpose in CSR).  Replaces scipy's csr_tocsc behind matrix1.T.tocsr()
+ * (s_plus.pyx:170,205-206).  With sort_rows != 0 every output row has ascending indices like scipy's; with 0
+ * the entries of a row are in arrival order, which is all the LEFT operand of the similarity kernel needs
+ * (only B's rows are searched for panel boundaries).  t_indptr must already hold the exclusive scan of
+ * the column counts (n_cols+1); cursor is n_cols int32 of scratch. */
 int spy_csr_transpose_dev(int32_t n_rows, int32_t n_cols, const int32_t *indptr, const int32_t *indices,
                           const float *data, const int32_t *t_indptr, int32_t *t_indices, float *t_data,
-                          int32_t *cursor, void *stream);
+                          int32_t *cursor, int sort_rows, void *stream);
 /* sort_indices (s_plus_utils.pyx:344,573): ascending column ids inside every row, in place */
 int spy_csr_sort_rows_dev(int32_t n_rows, const int32_t *indptr, int32_t *indices, float *data, void *stream);
 /* keep[i] != 0 entries only (eliminate_zeros s_plus.pyx:210-211 with keep = data != 0;

@@ -174,8 +174,9 @@ def _upload_index(ctx: Ctx, arr: np.ndarray):
     return ctx.h2d(arr)
 
 
-def transpose_csr(ctx: Ctx, m: DeviceCSR) -> DeviceCSR:
-    """CSR -> CSR of the transpose, rows sorted (scipy csr_tocsc behind s_plus.pyx:205-206)."""
+def transpose_csr(ctx: Ctx, m: DeviceCSR, sort: bool = True) -> DeviceCSR:
+    """CSR -> CSR of the transpose (scipy csr_tocsc behind s_plus.pyx:205-206); rows sorted like scipy's unless
+    sort=False (enough for the left operand of the similarity kernel, and a third of the transposition's time)."""
     torch = ctx.torch
     counts = ctx.empty(max(m.n_cols, 1), torch.int32)[: m.n_cols]
     _lib.check(ctx.lib.spy_csr_col_count_dev(m.nnz, _ptr(m.indices), m.n_cols, _ptr(counts), ctx.sptr))
@@ -184,8 +185,9 @@ def transpose_csr(ctx: Ctx, m: DeviceCSR) -> DeviceCSR:
     t_data = ctx.empty(m.nnz, torch.float32)
     cursor = ctx.empty(max(m.n_cols, 1), torch.int32)
     _lib.check(ctx.lib.spy_csr_transpose_dev(m.n_rows, m.n_cols, _ptr(m.indptr), _ptr(m.indices), _ptr(m.data),
-                                             _ptr(t_indptr), _ptr(t_indices), _ptr(t_data), _ptr(cursor), ctx.sptr))
-    return DeviceCSR(m.n_cols, m.n_rows, t_indptr, t_indices, t_data, sorted_rows=True)
+                                             _ptr(t_indptr), _ptr(t_indices), _ptr(t_data), _ptr(cursor), 1 if sort else 0,
+                                             ctx.sptr))
+    return DeviceCSR(m.n_cols, m.n_rows, t_indptr, t_indices, t_data, sorted_rows=bool(sort))
 
 
 def filter_csr(ctx: Ctx, m: DeviceCSR, col_mask=None, drop_zeros=False, values=None) -> DeviceCSR:
@@ -247,10 +249,10 @@ def upload_pair(ctx: Ctx, matrix1, matrix2):
     """A = matrix1 and B = matrix2 as device CSR.  With matrix2=None (B = matrix1.T, s_plus.pyx:169-170)
     the data crosses PCIe once and is transposed once on the GPU, whichever of CSR / CSC matrix1 is."""
     s1, t1 = upload_stored(ctx, matrix1)
-    if matrix2 is None:
-        other = transpose_csr(ctx, s1)
+    if matrix2 is None:  # A's row order is free; B is sorted later only if the plan has several panels
+        other = transpose_csr(ctx, s1, sort=False)
         return (other, s1) if t1 else (s1, other)
-    A = transpose_csr(ctx, s1) if t1 else s1
+    A = transpose_csr(ctx, s1, sort=False) if t1 else s1
     s2, t2 = upload_stored(ctx, matrix2)
     B = transpose_csr(ctx, s2) if t2 else s2
     return A, B

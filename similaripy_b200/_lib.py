@@ -61,7 +61,7 @@ SIGNATURES = {
     "spy_scan_tmp_bytes": (_i64, [_i64]),
     "spy_exclusive_scan_i32_dev": (C.c_int, [_i64, _vp, _vp, _vp, _vp]),
     "spy_exclusive_scan_i64_dev": (C.c_int, [_i64, _vp, _vp, _vp, _vp]),
-    "spy_csr_transpose_dev": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "spy_csr_transpose_dev": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp]),
     "spy_csr_sort_rows_dev": (C.c_int, [_i32, _vp, _vp, _vp, _vp]),
     "spy_csr_filter_count_dev": (C.c_int, [_i32, _vp, _vp, _vp, _vp, C.c_int, _vp, _vp]),
     "spy_csr_filter_compact_dev": (C.c_int, [_i32, _vp, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp]),
@@ -76,7 +76,7 @@ SIGNATURES = {
                                    C.c_int, C.c_int, _f64, _vp, _vp]),
 }
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 _lib = None
 
 

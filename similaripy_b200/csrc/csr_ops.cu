@@ -500,7 +500,7 @@ int spy_exclusive_scan_i64_dev(int64_t n, const int32_t *counts, int64_t *offset
 
 int spy_csr_transpose_dev(int32_t n_rows, int32_t n_cols, const int32_t *indptr, const int32_t *indices,
                           const float *data, const int32_t *t_indptr, int32_t *t_indices, float *t_data,
-                          int32_t *cursor, void *stream) {
+                          int32_t *cursor, int sort_rows, void *stream) {
     if (n_rows <= 0 || n_cols <= 0) return SPY_OK;
     cudaStream_t st = as_stream(stream);
     copy_i32_kernel<<<grid_for(n_cols, kThreads), kThreads, 0, st>>>(n_cols, t_indptr, cursor);
@@ -508,9 +508,11 @@ int spy_csr_transpose_dev(int32_t n_rows, int32_t n_cols, const int32_t *indptr,
     transpose_scatter_kernel<<<grid_for(n_rows, kWarpsPerBlock), kThreads, 0, st>>>(n_rows, indptr, indices, data, cursor,
                                                                                    t_indices, t_data);
     SPY_LAUNCH_OK();
-    int grid = n_cols < kB200SmCount * 8 ? n_cols : kB200SmCount * 8;
-    sort_rows_kernel<<<grid, kSortThreads, 0, st>>>(n_cols, t_indptr, t_indices, t_data);
-    SPY_LAUNCH_OK();
+    if (sort_rows) {  // the scatter lands in arrival order
+        int grid = n_cols < kB200SmCount * 8 ? n_cols : kB200SmCount * 8;
+        sort_rows_kernel<<<grid, kSortThreads, 0, st>>>(n_cols, t_indptr, t_indices, t_data);
+        SPY_LAUNCH_OK();
+    }
     return SPY_OK;
 }
 
