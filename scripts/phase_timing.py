@@ -9,15 +9,26 @@ import bench
 import similaripy_b200 as sim
 from similaripy_b200 import _engine
 
-scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
+cfg5 = len(sys.argv) > 1 and sys.argv[1] == "cfg5"
+scale = 1.0 if cfg5 else (float(sys.argv[1]) if len(sys.argv) > 1 else 1.0)
 tuning = {k: int(v) for k, v in (kv.split("=") for kv in sys.argv[2].split(","))} if len(sys.argv) > 2 else None
 dev = torch.device("cuda", 0)
 n_users, n_items = int(1_000_000 * scale), int(200_000 * scale)
 density = 1e-3 if scale == 1.0 else min(0.5, 1e-3 / scale ** 0.5)
 ip, ix, dv = bench.gen_urm_device(n_users, n_items, density, 2, dev)
 urm = sim.DeviceMatrix(_engine.DeviceCSR(n_users, n_items, ip, ix, dv, sorted_rows=True), False)
-urm = sim.bm25(urm, inplace=True)
-job = _engine.prepare_job(urm.T, None, l2=1.0, c1=0.5, c2=0.5, k=100, verbose=False, device=0, tuning=tuning)
+urm = sim.bm25(urm, inplace=True) if not cfg5 else None
+if cfg5:
+    import numpy as np
+    urm = None
+    ip, ix, dv = bench.gen_urm_device(5_000_000, 200_000, 1e-3, 5, dev)
+    u5 = sim.DeviceMatrix(_engine.DeviceCSR(5_000_000, 200_000, ip, ix, dv, sorted_rows=True), False)
+    ip, ix, dv = bench.gen_urm_device(200_000, 200_000, 5e-4, 55, dev)
+    st = sim.DeviceMatrix(_engine.DeviceCSR(200_000, 200_000, ip, ix, dv, sorted_rows=True), False)
+    rows = np.sort(np.random.default_rng(5).choice(5_000_000, size=200_000, replace=False)).astype(np.int32)
+    job = _engine.prepare_job(u5, st, k=100, target_rows=rows, filter_cols=u5, verbose=False, device=0, tuning=tuning)
+else:
+    job = _engine.prepare_job(urm.T, None, l2=1.0, c1=0.5, c2=0.5, k=100, verbose=False, device=0, tuning=tuning)
 for it in range(2):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(); job.run(); ev1.record(); torch.cuda.synchronize()

@@ -123,7 +123,7 @@ static int make_plan(const spy_knn_args &a, int device, Plan &pl) {
         if (a.b_nnz > 0 && a.b_rows > 0) {
             const double seg = (double)a.b_nnz / ((double)a.b_rows * pl.n_panels);
             const double want = seg * 0.65 / (2 * unroll_for(pl.threads));
-            G = want <= 5.7 ? 4 : want <= 11.4 ? 8 : want <= 22.7 ? 16 : 32;
+            G = want <= 2.9 ? 4 : want <= 11.4 ? 8 : want <= 22.7 ? 16 : 32;  // 4-lane groups only pay below ~18-entry segments
         }
     }
     if (G != 4 && G != 8 && G != 16 && G != 32) {

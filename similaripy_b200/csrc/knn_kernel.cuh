@@ -519,10 +519,12 @@ __device__ __forceinline__ unsigned drain_pass(const KnnDev &p, const FastRow &f
     const int n_iter = (width + S - 1) / S;
 
     // ---- phase 1: coarse test against the per-block minima; lane i of the warp holds the block of step i (yv) ----
-    const bool coarse = filter && (KIND == KIND_C || KIND == KIND_D) && p.y_block_min != nullptr && lo > 0.f && lc >= 0.f;
+    // (a raw dot product needs no Y at all: its bound is lo itself)
+    const bool coarse = filter && lo > 0.f &&
+                        (KIND == KIND_RAW || ((KIND == KIND_C || KIND == KIND_D) && p.y_block_min != nullptr && lc >= 0.f));
     if (coarse) {  // block-uniform
         for (int it = 0; it < n_iter; it++) {
-            const float bound = fmaf(lc, __shfl_sync(0xffffffffu, yv, it), la);
+            const float bound = (KIND == KIND_RAW) ? lo : fmaf(lc, __shfl_sync(0xffffffffu, yv, it), la);
             const int i = tid * 4 + it * S;
             if ((todo >> it & 1u) && i < wv) {
                 const unsigned a = acc32 + (unsigned)i * 4u;
@@ -583,11 +585,12 @@ __device__ __forceinline__ unsigned drain_pass(const KnnDev &p, const FastRow &f
 // Same for MODE_MATRIX target columns (s_plus.h:175-188): only the columns listed in the target row's sorted
 // list [tlo, thi) can be candidates.  A consumed slot is reset, which also makes duplicate list entries harmless.
 template <int NT>
-__device__ __forceinline__ void drain_pass_list(const KnnDev &p, float *acc, int base, int tlo, int thi, u64 *cand,
+__device__ __forceinline__ void drain_pass_list(const KnnDev &p, float *acc, int base, int width, int tlo, int thi, u64 *cand,
                                                 int *s_cnt, int *s_overflow) {
     bool overflow = false;
-    for (int q = tlo + threadIdx.x; q < thi; q += NT) {
+    for (int q = tlo + threadIdx.x; q < thi; q += NT) {  // the whole (sorted) list: only columns of this panel count
         const int col = __ldg(p.t_indices + q);
+        if (col < base || col >= base + width) continue;
         if (q > tlo && __ldg(p.t_indices + q - 1) == col) continue;  // one owner per column
         const float xy = acc[col - base];
         if (__float_as_uint(xy) == kSentinelBits) continue;
@@ -902,21 +905,20 @@ knn_flat_kernel(const __grid_constant__ KnnDev p) {
             fr.cD = p.l3 * sr.Xd;
 
             // ---------------- per-row filter matrix: erase filtered columns (s_plus.h:159-172) --
+            // one coalesced sweep over the row's filter list per panel (a binary search for the panel's range would
+            // be a chain of ~2 log2(n) dependent global loads in front of every drain)
             if (p.filter_mode == SPY_SEL_MATRIX) {
                 const int fs = __ldg(p.f_indptr + t), fe = __ldg(p.f_indptr + t + 1);
-                const int flo = lower_bound_dev(p.f_indices, fs, fe, base);
-                const int fhi = lower_bound_dev(p.f_indices, flo, fe, base + width);
-                for (int q = flo + tid; q < fhi; q += NT) acc[__ldg(p.f_indices + q) - base] = sentinel;
+                for (int q = fs + tid; q < fe; q += NT) {
+                    const int c = __ldg(p.f_indices + q) - base;
+                    if (c >= 0 && c < width) acc[c] = sentinel;
+                }
                 __syncthreads();
             }
 
             // ---------------- drain: pre-filter, similarity, threshold, top-k (s_plus.h:193-215) ----------
-            int tlo = 0, thi = 0;
-            if (p.target_mode == SPY_SEL_MATRIX) {
-                const int ts = __ldg(p.t_indptr + t), te = __ldg(p.t_indptr + t + 1);
-                tlo = lower_bound_dev(p.t_indices, ts, te, base);
-                thi = lower_bound_dev(p.t_indices, tlo, te, base + width);
-            }
+            int tlo = 0, thi = 0;  // the target row's list of admissible columns (matrix-mode target_cols)
+            if (p.target_mode == SPY_SEL_MATRIX) { tlo = __ldg(p.t_indptr + t); thi = __ldg(p.t_indptr + t + 1); }
             // steps of this panel the thread still has to drain: bit it <=> quad tid + it * NT exists
             unsigned todo = 0u;
             for (int it = 0; tid * 4 + it * NT * 4 < width; it++) todo |= 1u << it;
@@ -1005,7 +1007,7 @@ knn_flat_kernel(const __grid_constant__ KnnDev p) {
             for (int attempt = 0; attempt < 2; attempt++) {
                 const float lo_use = spec ? reject_bound(p, tau_s > tau ? tau_s : tau) : lo;
                 for (;;) {
-                    if (p.target_mode == SPY_SEL_MATRIX) drain_pass_list<NT>(p, acc, base, tlo, thi, cand, &s_cnt, &s_overflow);
+                    if (p.target_mode == SPY_SEL_MATRIX) drain_pass_list<NT>(p, acc, base, width, tlo, thi, cand, &s_cnt, &s_overflow);
                     else todo = drain_pass<NT, KIND>(p, fr, acc32, base, width, spec ? fmaxf(lo_use, lo) : lo, yv, cand, &s_cnt,
                                                      &s_overflow, todo, spec);
 #if SPY_PHASE_TIMING
@@ -1068,6 +1070,11 @@ knn_flat_kernel(const __grid_constant__ KnnDev p) {
             }
         }
 
+        // the next row's split points (one 32-byte sector per entry holds all panels) -> L2, before they are needed
+        if (SPY_PREFETCH && s_next[0] < p.n_targets && tid < s_next[4] - s_next[3]) {
+            const int *sp = (p.n_panels == 1) ? p.b_indptr + u_n : p.b_split + (size_t)u_n * p.split_stride;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(sp));
+        }
         // ---------------- final selection and slab write (s_plus.h:443-450) ----------------
         __syncthreads();
         select_topk<NT>(cand, n_eval, p.k, tmp, kTmpCap, &s_cnt, &s_tau, &s_live, &s_pivot);
