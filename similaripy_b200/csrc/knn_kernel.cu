@@ -81,11 +81,11 @@ struct Plan {
 static int make_plan(const spy_knn_args &a, int device, Plan &pl) {
     DeviceInfo di = device_info(device);
     pl.threads = a.threads ? a.threads : 1024;
-    if (pl.threads != 512 && pl.threads != 1024) {
-        set_error("threads must be 512 or 1024 (got %d)", pl.threads);
+    if (pl.threads != 512 && pl.threads != 768 && pl.threads != 1024) {
+        set_error("threads must be 512, 768 or 1024 (got %d)", pl.threads);
         return SPY_ERR_INVALID;
     }
-    pl.ctas_per_sm = 1024 / pl.threads;  // 64 registers per thread either way
+    pl.ctas_per_sm = pl.threads == 512 ? 2 : 1;  // 512 x 2 and 1024 x 1: 64 registers per thread; 768 x 1: 80
     pl.cap = std::max(2048, next_pow2(2 * std::max(a.k, 1)));
     pl.cand_smem = (size_t)pl.cap * 8 <= 65536;
     // staged target-row chunk: 8 bytes per thread (doubles as the selection's scratch)

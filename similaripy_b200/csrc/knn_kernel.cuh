@@ -173,16 +173,19 @@ __device__ __noinline__ void rank_and_publish(const u64 *buf, int n, int k, u64 
     if (tid == 0) *s_live = 0;
     __syncthreads();
     int live = 0;
-    if (P <= NT) {
-        const int tpk = NT / P;  // power of two <= 32: the threads of a key are neighbouring lanes
-        const int i = tid / tpk, part = tid & (tpk - 1);
-        const u64 key = (i < n) ? buf[i] : 0ull;
-        int cnt = 0;
-        for (int j = part; j < n; j += tpk) cnt += (buf[j] > key) ? 1 : 0;
-        for (int o = tpk >> 1; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-        if (part == 0 && key != 0ull) {
-            live = 1;
-            if (cnt < k) cand[cnt] = key;
+    constexpr int NTP = NT >= 1024 ? 1024 : 512;  // largest power of two <= NT: the threads that rank
+    if (P <= NTP) {
+        if (tid < NTP) {
+            const int tpk = NTP / P;  // power of two <= 32: the threads of a key are neighbouring lanes
+            const int i = tid / tpk, part = tid & (tpk - 1);
+            const u64 key = (i < n) ? buf[i] : 0ull;
+            int cnt = 0;
+            for (int j = part; j < n; j += tpk) cnt += (buf[j] > key) ? 1 : 0;
+            for (int o = tpk >> 1; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+            if (part == 0 && key != 0ull) {
+                live = 1;
+                if (cnt < k) cand[cnt] = key;
+            }
         }
     } else {
         for (int i = tid; i < n; i += NT) {
@@ -775,7 +778,7 @@ __device__ __forceinline__ bool accumulate_chunk(const ExpandArgs x, int n, cons
 //             (dot product, column) and evaluated densely afterwards -- computeSimilarity with its IEEE
 //             division runs with all lanes busy -- then the sampled selection keeps the best k.
 template <int NT, int KIND, bool CAND_SMEM, int G>
-__global__ void __launch_bounds__(NT, 1024 / NT)
+__global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1)
 knn_flat_kernel(const __grid_constant__ KnnDev p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *acc = reinterpret_cast<float *>(smem_raw);
