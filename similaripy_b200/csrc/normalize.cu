@@ -140,24 +140,36 @@ __global__ void tfidf_apply_kernel(long long n_rows, T *__restrict__ data, const
     }
 }
 
-// avg_doc_len: sequential sum in row order and storage precision (normalization.pyx:297,315,323).
-// One warp: coalesced loads of 32 values, then a serial add chain fed by shuffles.
+// avg_doc_len: sequential sum in row order and storage precision (normalization.pyx:297,315,323).  The add chain is
+// inherently serial (one dependent add per row: ~4 cycles each); everything else is taken off it: the whole CTA
+// streams the next tile into shared memory (coalesced, deep memory parallelism) while thread 0 adds the current one.
+constexpr int kMeanTile = 2048;  // 2 x 2048 doubles = 32 KB of static shared memory
 template <typename T>
-__global__ void sequential_mean_kernel(long long n, const T *__restrict__ x, T *__restrict__ out) {
-    const int lane = threadIdx.x;
+__global__ void __launch_bounds__(1024) sequential_mean_kernel(long long n, const T *__restrict__ x, T *__restrict__ out) {
+    __shared__ T buf[2][kMeanTile];
+    const int tid = threadIdx.x;
     T acc = (T)0;
-    for (long long c0 = 0; c0 < n; c0 += 32) {
-        const long long i = c0 + lane;
-        const T v = (i < n) ? x[i] : (T)0;
-        if (n - c0 >= 32) {
-#pragma unroll
-            for (int l = 0; l < 32; l++) acc += __shfl_sync(0xffffffffu, v, l);
-        } else {
-            const int m = (int)(n - c0);
-            for (int l = 0; l < m; l++) acc += __shfl_sync(0xffffffffu, v, l);
+    for (int i = tid; i < kMeanTile; i += 1024) buf[0][i] = (i < n) ? x[i] : (T)0;
+    __syncthreads();
+    int cur = 0;
+    for (long long c0 = 0; c0 < n; c0 += kMeanTile) {
+        const long long nxt = c0 + kMeanTile;
+        if (nxt < n)
+            for (int i = tid; i < kMeanTile; i += 1024) buf[cur ^ 1][i] = (nxt + i < n) ? x[nxt + i] : (T)0;
+        if (tid == 0) {
+            const int m = (int)((n - c0 < kMeanTile) ? (n - c0) : kMeanTile);
+            const T *b = buf[cur];
+            int i = 0;
+            for (; i + 8 <= m; i += 8) {  // loads first, then the dependent adds in row order
+                const T v0 = b[i], v1 = b[i + 1], v2 = b[i + 2], v3 = b[i + 3], v4 = b[i + 4], v5 = b[i + 5], v6 = b[i + 6], v7 = b[i + 7];
+                acc += v0; acc += v1; acc += v2; acc += v3; acc += v4; acc += v5; acc += v6; acc += v7;
+            }
+            for (; i < m; i++) acc += b[i];
         }
+        __syncthreads();
+        cur ^= 1;
     }
-    if (lane == 0) out[0] = acc / (T)n;
+    if (tid == 0) out[0] = acc / (T)n;
 }
 
 template <typename T, typename I>
@@ -219,7 +231,7 @@ static int run_tfidf_bm25(bool bm25, long long n_rows, long long n_cols, T *data
                                                        (const T *)sc.idf, tf_mode, log_logbase);
         SPY_LAUNCH_OK();
     } else {
-        sequential_mean_kernel<T><<<1, 32, 0, st>>>(n_rows, (const T *)sc.doc_len, (T *)sc.avg);
+        sequential_mean_kernel<T><<<1, 1024, 0, st>>>(n_rows, (const T *)sc.doc_len, (T *)sc.avg);
         SPY_LAUNCH_OK();
         bm25_apply_kernel<T, I><<<grid, kNT, 0, st>>>(n_rows, data, indices, indptr, (const T *)sc.doc_len,
                                                       (const T *)sc.idf, (const T *)sc.avg, (T)k1, (T)b, (T)delta,
