@@ -285,3 +285,35 @@ def test_dense_candidates_binary_integer_exact():
     got = sim.dot_product(a, urm, k=150, target_rows=rows, verbose=False, format_output="csr", tuning=dict(panel_width=8192))
     ref = oracle.similarity("dot_product", a, urm, k=150, target_rows=rows, verbose=False, format_output="csr")
     assert_topk_parity(ref, got, k=150, rtol=0.0, what="dense integer dot")
+
+
+# ---- skewed (power-law) data: a few very long rows and columns, most of them short -------------------------------------
+def _zipf_urm(n_users, n_items, nnz, seed):
+    rng = np.random.default_rng(seed)
+    pu = 1.0 / np.arange(1, n_users + 1) ** 0.9
+    pi = 1.0 / np.arange(1, n_items + 1) ** 1.1
+    u = rng.choice(n_users, size=nnz, p=pu / pu.sum())
+    i = rng.choice(n_items, size=nnz, p=pi / pi.sum())
+    m = sp.csr_array((np.ones(nnz, dtype=np.float32), (rng.permutation(n_users)[u], rng.permutation(n_items)[i])),
+                     shape=(n_users, n_items))
+    m.sum_duplicates()
+    m.data = (1.0 + rng.random(m.nnz)).astype(np.float32)  # counts replaced by ratings in [1, 2)
+    return m
+
+
+@pytest.mark.parametrize("name,kw", [("cosine", {}), ("rp3beta", dict(alpha=0.7, beta=0.5)), ("jaccard", dict(binary=True)),
+                                     ("dot_product", {})], ids=["cosine", "rp3beta", "jaccard_binary", "dot"])
+@pytest.mark.parametrize("tuning", [None, dict(threads=512, panel_width=1024)], ids=["plan", "panels"])
+def test_power_law_data(name, kw, tuning):
+    """Head items are bought by most users (A rows of several thousand entries: many staging chunks, dynamic batch
+    claims), head users own hundreds of items (B segments far longer than the group width), the tail is nearly empty."""
+    urm = _zipf_urm(6000, 5000, 150_000, 13)
+    a = urm.T.tocsr()
+    assert np.diff(a.indptr).max() > 2600  # longer than two staging chunks of 1280 entries
+    rows = np.concatenate([np.argsort(-np.diff(a.indptr))[:40], np.arange(0, 5000, 53)]).astype(np.int32)
+    rows = np.unique(rows)
+    k = 60
+    got = getattr(sim, name)(a, urm, k=k, target_rows=rows, verbose=False, format_output="csr", tuning=tuning, **kw)
+    ref = oracle.similarity(name, a, urm, k=k, target_rows=rows, verbose=False, format_output="csr", **kw)
+    # jaccard on binary data is all ties: values must agree exactly, columns only outside the tie band
+    assert_topk_parity(ref, got, k=k, rtol=1e-5, what=f"zipf {name} {tuning}")
