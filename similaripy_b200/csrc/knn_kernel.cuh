@@ -12,17 +12,19 @@
 //     at shared-memory instead of L2-cache scale, s_plus.h:305-311);
 //   * panel boundaries inside every sorted row of B are precomputed once (b_split) --
 //     the reference does a std::lower_bound per (target row, block, B row), s_plus.h:381-394;
-//   * the products of (target row, panel) are flattened into one index space by a block scan of
-//     the segment lengths, so every lane of every warp streams 8-byte (column, value) pairs
-//     whatever the segment lengths are; accumulation is a shared-memory float atomic
-//     (measured 538-605 Gproducts/s on B200, profiles/microbench/accum_bench_r01.txt);
+//   * a group of G lanes owns one entry (u, v) of the target row at a time and streams the run of B-row u
+//     that falls into the panel as 16-byte gathers of two (column, value) pairs; accumulation is a
+//     shared-memory float add (measured 540 Gproducts/s on B200 on its own, profiles/microbench/);
 //   * "touched" is encoded in the accumulator itself: slots start at -0.0f, and
 //     (-0.0f) + x == x, so a slot whose bits are still 0x80000000 was never written
 //     (the reference keeps a touched-list, s_plus.h:112-117);
-//   * the drain applies filter / target selectors, computeSimilarity (s_plus.h:129-156) with
-//     the same operation order and no FMA contraction, the threshold test (s_plus.h:206), and
-//     feeds a running-threshold candidate buffer; a bitonic sort compacts it to the best k
-//     whenever it fills and once at the end of the row;
+//   * the drain applies filter / target selectors and a division-free pre-filter against the running
+//     k-th best (per-block minima of Y first, per slot second), buffers the survivors, then computes
+//     computeSimilarity (s_plus.h:129-156) with the same operation order and no FMA contraction and the
+//     threshold test (s_plus.h:206) for the whole buffer; sampling rounds shrink the buffer when it
+//     fills, a rank sort orders the best k at the end of the row;
+//   * a row's first panel is drained with a speculative bound taken from a sample and validated
+//     before anything it rejected is discarded;
 //   * ties are resolved deterministically: larger value first, then smaller column id.
 #pragma once
 #include "common.cuh"
@@ -351,34 +353,6 @@ __device__ __forceinline__ float reject_bound(const KnnDev &p, u64 tau) {
     return bound - fabsf(bound) * 1e-4f - 1e-37f;
 }
 
-// Exclusive block scan of one int per thread (NT <= 1024).  Two barriers.  wtot has 33 ints.
-template <int NT>
-__device__ __forceinline__ int block_exclusive_scan(int v, int *wtot, int &total) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int incl = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-    }
-    if (lane == 31) wtot[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-        const int w = (lane < NT / 32) ? wtot[lane] : 0;
-        int wi = w;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, wi, o);
-            if (lane >= o) wi += t;
-        }
-        wtot[lane] = wi - w;
-        if (lane == 31) wtot[32] = wi;
-    }
-    __syncthreads();
-    total = wtot[32];
-    return wtot[warp] + incl - v;
-}
-
 // shared-memory float add on a 32-bit shared address: LDS / FADD / ATOMS.CAST.SPIN loop, 543 Gadd/s on
 // B200 (profiles/microbench); the plain atomicAdd(float*) form recomputes the shared window base per call.
 __device__ __forceinline__ void smem_add_f32(unsigned addr, float x) {
@@ -631,47 +605,17 @@ struct ExpandArgs {  // what the expansion needs of KnnDev, by value: the routin
 #ifndef SPY_PREFETCH
 #define SPY_PREFETCH 1
 #endif
-#ifndef SPY_BATCH_CAS
-#define SPY_BATCH_CAS 0
-#endif
-__device__ __forceinline__ float lds32(unsigned addr) {
-    float v;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ unsigned cas_shared(unsigned addr, unsigned expect, unsigned desired) {
-    unsigned got;
-    asm volatile("atom.shared.cas.b32 %0, [%1], %2, %3;" : "=r"(got) : "r"(addr), "r"(expect), "r"(desired));
-    return got;
-}
 __device__ __forceinline__ uint4 ldg128(const uint2 *ptr) {
     return __ldg(reinterpret_cast<const uint4 *>(ptr));
 }
 
-// N float adds to N (pairwise distinct per lane) shared-memory addresses with the compare-and-swap loops
-// interleaved: one round issues every pending load, then every pending CAS, so a lane has N independent
-// shared-memory operations in flight instead of one (the plain red.shared.add.f32 is an LDS / FADD /
-// ATOMS.CAST.SPIN loop per add, each waiting for the previous one).  `pend` has bit r set for a live add.
+// N float adds to N shared-memory addresses; `pend` has bit r set for a live add.  red.shared.add.f32 is an
+// LDS / FADD / ATOMS.CAST.SPIN loop in SASS (interleaving the loops by hand with atom.shared.cas was 3x slower).
 template <int N>
 __device__ __forceinline__ void smem_add_batch(const unsigned (&addr)[N], const float (&x)[N], unsigned pend) {
-#if SPY_BATCH_CAS
-    while (pend) {
-        float old[N];
-#pragma unroll
-        for (int r = 0; r < N; r++)
-            if (pend & (1u << r)) old[r] = lds32(addr[r]);
-#pragma unroll
-        for (int r = 0; r < N; r++)
-            if (pend & (1u << r)) {
-                const unsigned o = __float_as_uint(old[r]);
-                if (cas_shared(addr[r], o, __float_as_uint(__fadd_rn(old[r], x[r]))) == o) pend &= ~(1u << r);
-            }
-    }
-#else
 #pragma unroll
     for (int r = 0; r < N; r++)
         if (pend & (1u << r)) smem_add_f32(addr[r], x[r]);
-#endif
 }
 
 // Bounds of a group's FIRST segment in the NEXT panel, fetched while the current panel is being accumulated

@@ -5,7 +5,7 @@ exceptions; each function only picks the constants of the one fused kernel behin
 
 Three keyword-only extras exist on every function and default to the reference behaviour:
 ``device`` (CUDA device index, default: current device / $SIMILARIPY_B200_DEVICE),
-``tuning`` (dict: threads / lanes / panel_width overrides for the launch plan) and
+``tuning`` (dict: threads / group / panel_width overrides for the launch plan) and
 ``on_device`` (return a ``DeviceMatrix`` that stays in HBM instead of a scipy matrix; inputs may be
 ``DeviceMatrix`` handles from ``similaripy_b200.to_device`` as well, so calls chain without PCIe trips).
 """
