@@ -27,6 +27,14 @@ out = [f"ncu --metrics gpu__time_duration.sum --clock-control none -c 400: pytho
        f"{'kernel':70s} {'launches':>8s} {'total ' + unit:>16s} {'share':>7s}"]
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     out.append(f"{k[:70]:70s} {v[0]:8d} {v[1]:16.0f} {100 * v[1] / tot:6.2f}%")
+# share of the hot kernel among the kernels of the timed step only (the command also generates the data and runs bm25)
+setup = ("sequential_mean", "bm25_apply", "doclen_df", "idf_kernel", "at_cuda", "native::", "cuda::", "at::", "cub::", "sort_rows")
+step = {k: v for k, v in agg.items() if "spy::" in k and not any(x in k for x in setup)}
+step_tot = sum(v[1] for v in step.values())
+hot = sum(v[1] for k, v in step.items() if "knn_flat_kernel" in k)
+out.append("")
+out.append(f"kernels of the timed step only (without data generation and bm25): hot kernel {100 * hot / step_tot:.1f} % of {step_tot / 1e6:.1f} ms "
+           f"-- bench.py reports kernel_share_of_step = {json.load(open(os.path.join(src, f'bench_{tag}.json')))['roofline']['kernel_share_of_step']}")
 open(os.path.join(dst, f"launches_{tag}_cfg2.txt"), "w").write("\n".join(out) + "\n")
 # ncu full summary
 rep = os.path.join(src, f"prof_knn_{tag}.ncu-rep")
