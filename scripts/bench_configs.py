@@ -3,7 +3,7 @@
 synthetic operands generated on the device, a uniform sample of the target rows (rows are independent),
 CUDA-event time of the hot kernel, algorithmic bytes -> fraction of the measured HBM peak.
 usage: python scripts/bench_configs.py [cfg3 cfg4 cfg5 ...]"""
-import json, os, sys, time
+import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np

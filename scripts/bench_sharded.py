@@ -5,7 +5,6 @@ Launch: python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-a
 import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-import numpy as np
 import torch
 import torch.distributed as dist
 import bench

@@ -6,7 +6,6 @@ dtype coercion, copy unless ``inplace``, ``axis=0`` via transpose, always a CSR 
 """
 from __future__ import annotations
 
-import ctypes as C
 from math import e
 
 import numpy as np
