@@ -68,6 +68,15 @@ __global__ void __launch_bounds__(1024) bench(const int* __restrict__ cols, cons
                     carry = __uint_as_float(got);
                 } while (__float_as_uint(carry) != 0x80000000u);
             }
+            else if (MODE == 14) {  // exact fixed point on native integer adds: two 32-bit limbs per slot (8 bytes), 2 ATOMS.ADD per product
+                // value = hi * 2^20 + lo in units of the grid; |term| < 2^39 grid units, lo limb takes the low 20 bits (signed split)
+                const float scaled = vi[j] * 1048576.0f * 1024.0f;          // stand-in for product * 2^scale
+                const long long q = __float2ll_rn(scaled);
+                const int lo = (int)(q & 0xfffff), hi = (int)(q >> 20);
+                unsigned a = sbase + (ci[j] % (W / 2)) * 8;
+                asm volatile("red.shared.add.s32 [%0], %1;" :: "r"(a), "r"(lo) : "memory");
+                asm volatile("red.shared.add.s32 [%0], %1;" :: "r"(a + 4), "r"(hi) : "memory");
+            }
             else if (MODE == 12) { unsigned a = sbase + ((ci[j] & ~31) | lane) * 4; asm volatile("red.shared.add.f32 [%0], %1;" :: "r"(a), "f"(vi[j]) : "memory"); }
         }
         if (MODE == 11) {  // swap-carry, the 4 adds of the step interleaved
@@ -142,6 +151,7 @@ int main() {
         run<11>("swap-carry add, 4 interleaved", thr, cps, W, cols, vals, N, gacc, out, nsm);
         run<12>("red.shared.add.f32, distinct banks", thr, cps, W, cols, vals, N, gacc, out, nsm);
         run<13>("swap-carry add, distinct banks", thr, cps, W, cols, vals, N, gacc, out, nsm);
+        run<14>("fixed point, 2 native int adds (8 B slots)", thr, cps, W, cols, vals, N, gacc, out, nsm);
         if (W == 49152) { run<1>("smem float atomicAdd (CAS)", 512, 1, W, cols, vals, N, gacc, out, nsm); run<1>("smem float atomicAdd (CAS)", 256, 1, W, cols, vals, N, gacc, out, nsm); }
         else { run<1>("smem float atomicAdd (CAS)", 1024, 2, W, cols, vals, N, gacc, out, nsm); run<1>("smem float atomicAdd (CAS)", 256, 2, W, cols, vals, N, gacc, out, nsm);}
     }
