@@ -266,7 +266,7 @@ def test_dense_candidates_overflow_paths(name, kw, tuning):
     assert stats["full_rows"] >= 200
 
 
-@pytest.mark.parametrize("k", [1, 7, 700, 3000])
+@pytest.mark.parametrize("k", [1, 7, 700, 3000, 5000])  # 5000: candidate buffer in global memory
 def test_dense_candidates_k_extremes(k):
     urm = _dense_urm()
     a = urm.T.tocsr()
