@@ -1,0 +1,24 @@
+"""Workload for compute-sanitizer (memcheck / racecheck): dense candidate sets (buffer overflow, speculative bound, several
+panels, both CTA shapes), matrix filter / target selectors, normalizers.
+    compute-sanitizer --tool memcheck  python scripts/sanitize_workload.py
+    compute-sanitizer --tool racecheck python scripts/sanitize_workload.py
+Round 1 on B200: 0 errors, 0 hazards."""
+import numpy as np, scipy.sparse as sp, sys
+sys.path.insert(0, '/root/repo')
+import similaripy_b200 as sim
+rng = np.random.default_rng(5)
+# dense candidates: overflow + speculation + several panels, plus a matrix filter and a matrix target
+urm = sp.random_array((800, 14000), density=0.03, format="csr", dtype=np.float32, random_state=rng)
+a = urm.T.tocsr()
+rows = list(range(0, 14000, 700))
+for name, kw in (("cosine", {}), ("rp3beta", dict(alpha=0.9, beta=0.4)), ("jaccard", {}), ("dot_product", {})):
+    for tuning in (None, dict(panel_width=2048), dict(threads=512, panel_width=1024, group=4)):
+        r = getattr(sim, name)(a, urm, k=50, target_rows=rows, verbose=False, format_output="csr", tuning=tuning, **kw)
+print("dense ok", r.nnz)
+u2 = sp.random_array((300, 500), density=0.05, format="csr", dtype=np.float32, random_state=rng)
+s2 = sp.random_array((500, 500), density=0.06, format="csr", dtype=np.float32, random_state=rng)
+r = sim.dot_product(u2, s2, k=12, filter_cols=u2, verbose=False, format_output="csr")
+tm = sp.random_array((300, 500), density=0.3, format="csr", dtype=np.float32, random_state=rng)
+r = sim.dot_product(u2, s2, k=12, target_cols=tm, verbose=False, format_output="coo")
+w = sim.bm25(u2); w = sim.tfidf(u2); w = sim.normalize(u2, "l1")
+print("selectors + normalizers ok")
