@@ -599,6 +599,12 @@ struct ExpandArgs {  // what the expansion needs of KnnDev, by value: the routin
 #else
 #define SPY_TICK(id) do { } while (0)
 #endif
+// one more sampling round right after a validated speculative bound (tighter bound for the later panels).  On cfg2
+// the full library measures the same with it on (199.3 ms) and off (200.3 ms); kept on, which is the build the
+// evidence under profiles/r01 was taken with
+#ifndef SPY_SHARPEN
+#define SPY_SHARPEN 1
+#endif
 #ifndef SPY_SPECULATE
 #define SPY_SPECULATE 1
 #endif
@@ -998,7 +1004,7 @@ knn_flat_kernel(const __grid_constant__ KnnDev p) {
                     if (tau_s > tau) { tau = tau_s; lo = reject_bound(p, tau); }
                     for (int i = tid * 4; i < width; i += NT * 4) sts128(acc32 + (unsigned)i * 4u, sentinel4);  // clear the panel
                     __syncthreads();  // before anyone accumulates the next panel into it
-                    if (n_eval > 2 * p.k) {  // sharpen the bound for the panels to come (one sampling round)
+                    if (SPY_SHARPEN && n_eval > 2 * p.k) {  // sharpen the bound for the panels to come (one sampling round)
                         tighten_topk<NT>(cand, n_eval, p.k, tmp, kTmpCap, &s_cnt, &s_tau, &s_live, &s_pivot);
                         staged_c0 = -1;
                         tau = s_tau;
