@@ -611,6 +611,9 @@ struct ExpandArgs {  // what the expansion needs of KnnDev, by value: the routin
 #ifndef SPY_PREFETCH
 #define SPY_PREFETCH 1
 #endif
+#ifndef SPY_EARLY_GATHER
+#define SPY_EARLY_GATHER 0  // measured next round (see accumulate_chunk)
+#endif
 __device__ __forceinline__ uint4 ldg128(const uint2 *ptr) {
     return __ldg(reinterpret_cast<const uint4 *>(ptr));
 }
@@ -676,6 +679,48 @@ __device__ __forceinline__ bool accumulate_chunk(const ExpandArgs x, int n, cons
     nxt.s = e; nxt.valid = want_next;
     bool first_pass = true;
     while (base0 < n) {  // warp-uniform
+#if SPY_EARLY_GATHER
+        // the pass's first gathers go out BEFORE the claim (a shared-memory atomic + shuffle round trip), the far bounds
+        // fetch and the L2 prefetch, which then run in the shadow of the gather latency instead of in front of it
+        const float v = (idx < n) ? st_v[idx] : 0.f;
+        const int sa = s & ~1;  // pairs are 8 bytes: an even position is 16-byte aligned
+        const int maxspan = __reduce_max_sync(0xffffffffu, e - sa);
+        any |= e > s;
+        uint4 pr[U];
+        auto gather = [&](int b) {
+            const int q0 = sa + b + 2 * gl;
+#pragma unroll
+            for (int r = 0; r < U; r++)
+                if (q0 + 2 * G * r < e) pr[r] = ldg128(x.b_pairs + q0 + 2 * G * r);  // the array is padded by one pair
+        };
+        if (maxspan > 0) gather(0);
+        base2 = n;
+        if (base1 < n) {  // claim the batch of the pass after next
+            if ((tid & 31) == 0) base2 = atomicAdd(next_entry, GPW);
+            base2 = __shfl_sync(0xffffffffu, base2, 0);
+        }
+        fetch(base2 + gw, s2, e2);
+        if (!first_pass) prefetch_l2(s1, e1);  // its bounds were fetched a whole pass ago
+        for (int b = 0; b < maxspan;) {
+            const int q0 = sa + b + 2 * gl;
+            unsigned addr[2 * U];
+            float val[2 * U];
+            unsigned pend = 0u;
+#pragma unroll
+            for (int r = 0; r < U; r++) {
+                const int q = q0 + 2 * G * r;
+                addr[2 * r] = accb32 + pr[r].x * 4u;
+                val[2 * r] = __fmul_rn(__uint_as_float(pr[r].y), v);
+                addr[2 * r + 1] = accb32 + pr[r].z * 4u;
+                val[2 * r + 1] = __fmul_rn(__uint_as_float(pr[r].w), v);
+                if (q >= s && q < e) pend |= 1u << (2 * r);
+                if (q + 1 < e) pend |= 1u << (2 * r + 1);  // q + 1 >= s always (q >= sa >= s - 1)
+            }
+            smem_add_batch<2 * U>(addr, val, pend);
+            b += 2 * G * U;
+            if (b < maxspan) gather(b);
+        }
+#else
         base2 = n;
         if (base1 < n) {  // claim the batch of the pass after next
             if ((tid & 31) == 0) base2 = atomicAdd(next_entry, GPW);
@@ -708,6 +753,7 @@ __device__ __forceinline__ bool accumulate_chunk(const ExpandArgs x, int n, cons
             }
             smem_add_batch<2 * U>(addr, val, pend);
         }
+#endif
         if (first_pass) { prefetch_l2(s1, e1); first_pass = false; }
         s = s1; e = e1; s1 = s2; e1 = e2;
         base0 = base1; base1 = base2;
@@ -776,27 +822,39 @@ __device__ SPY_TWOSEG_INLINE bool accumulate_chunk_two(const ExpandArgs x, int n
     };
     bool first_pass = true;
     while (base0 < n) {  // warp-uniform
-        base2 = n;
-        if (base1 < n) {  // claim the entries of the pass after next
-            if (lane == 0) base2 = atomicAdd(next_entry, 2 * GPW);
-            base2 = __shfl_sync(0xffffffffu, base2, 0);
-        }
-        if (role >= 2) fetch(base2 + (role & 1) * GPW + gw, fs, fe);
-        if (!first_pass) prefetch_next();
         const int iA = base0 + gw, iB = iA + GPW;
         const float vA = (iA < n) ? st_v[iA] : 0.f, vB = (iB < n) ? st_v[iB] : 0.f;
         const int saA = sA & ~1, saB = sB & ~1;  // pairs are 8 bytes: an even position is 16-byte aligned
         const int maxspan = __reduce_max_sync(0xffffffffu, max(eA - saA, eB - saB));
         any |= (eA > sA) | (eB > sB);
-        for (int b = 0; b < maxspan; b += 2 * G * U) {
+        uint4 pa[U], pb[U];
+        auto gather = [&](int b) {
             const int qA = saA + b + 2 * gl, qB = saB + b + 2 * gl;
-            uint4 pa[U], pb[U];
 #pragma unroll
             for (int r = 0; r < U; r++)
                 if (qA + 2 * G * r < eA) pa[r] = ldg128(x.b_pairs + qA + 2 * G * r);  // the array is padded by one pair
 #pragma unroll
             for (int r = 0; r < U; r++)
                 if (qB + 2 * G * r < eB) pb[r] = ldg128(x.b_pairs + qB + 2 * G * r);
+        };
+        auto housekeeping = [&]() {  // claim the entries of the pass after next, fetch their bounds, prefetch the next pass's pairs
+            base2 = n;
+            if (base1 < n) {
+                if (lane == 0) base2 = atomicAdd(next_entry, 2 * GPW);
+                base2 = __shfl_sync(0xffffffffu, base2, 0);
+            }
+            if (role >= 2) fetch(base2 + (role & 1) * GPW + gw, fs, fe);
+            if (!first_pass) prefetch_next();
+        };
+#if SPY_EARLY_GATHER
+        if (maxspan > 0) gather(0);  // in flight while the claim's atomic + shuffle round trip runs
+        housekeeping();
+#else
+        housekeeping();
+        if (maxspan > 0) gather(0);
+#endif
+        for (int b = 0; b < maxspan;) {
+            const int qA = saA + b + 2 * gl, qB = saB + b + 2 * gl;
             unsigned addr[2 * U];
             float val[2 * U];
             unsigned pend = 0u;
@@ -823,6 +881,8 @@ __device__ SPY_TWOSEG_INLINE bool accumulate_chunk_two(const ExpandArgs x, int n
                 if (q + 1 < eB) pend |= 1u << (2 * r + 1);
             }
             smem_add_batch<2 * U>(addr, val, pend);
+            b += 2 * G * U;
+            if (b < maxspan) gather(b);
         }
         if (first_pass) { prefetch_next(); first_pass = false; }
         // next pass: its bounds come from the role 0 / 1 lanes of the group; those lanes take over what roles 2 / 3 hold
