@@ -611,9 +611,6 @@ struct ExpandArgs {  // what the expansion needs of KnnDev, by value: the routin
 #ifndef SPY_PREFETCH
 #define SPY_PREFETCH 1
 #endif
-#ifndef SPY_EARLY_GATHER
-#define SPY_EARLY_GATHER 0  // measured next round (see accumulate_chunk)
-#endif
 __device__ __forceinline__ uint4 ldg128(const uint2 *ptr) {
     return __ldg(reinterpret_cast<const uint4 *>(ptr));
 }
@@ -679,48 +676,6 @@ __device__ __forceinline__ bool accumulate_chunk(const ExpandArgs x, int n, cons
     nxt.s = e; nxt.valid = want_next;
     bool first_pass = true;
     while (base0 < n) {  // warp-uniform
-#if SPY_EARLY_GATHER
-        // the pass's first gathers go out BEFORE the claim (a shared-memory atomic + shuffle round trip), the far bounds
-        // fetch and the L2 prefetch, which then run in the shadow of the gather latency instead of in front of it
-        const float v = (idx < n) ? st_v[idx] : 0.f;
-        const int sa = s & ~1;  // pairs are 8 bytes: an even position is 16-byte aligned
-        const int maxspan = __reduce_max_sync(0xffffffffu, e - sa);
-        any |= e > s;
-        uint4 pr[U];
-        auto gather = [&](int b) {
-            const int q0 = sa + b + 2 * gl;
-#pragma unroll
-            for (int r = 0; r < U; r++)
-                if (q0 + 2 * G * r < e) pr[r] = ldg128(x.b_pairs + q0 + 2 * G * r);  // the array is padded by one pair
-        };
-        if (maxspan > 0) gather(0);
-        base2 = n;
-        if (base1 < n) {  // claim the batch of the pass after next
-            if ((tid & 31) == 0) base2 = atomicAdd(next_entry, GPW);
-            base2 = __shfl_sync(0xffffffffu, base2, 0);
-        }
-        fetch(base2 + gw, s2, e2);
-        if (!first_pass) prefetch_l2(s1, e1);  // its bounds were fetched a whole pass ago
-        for (int b = 0; b < maxspan;) {
-            const int q0 = sa + b + 2 * gl;
-            unsigned addr[2 * U];
-            float val[2 * U];
-            unsigned pend = 0u;
-#pragma unroll
-            for (int r = 0; r < U; r++) {
-                const int q = q0 + 2 * G * r;
-                addr[2 * r] = accb32 + pr[r].x * 4u;
-                val[2 * r] = __fmul_rn(__uint_as_float(pr[r].y), v);
-                addr[2 * r + 1] = accb32 + pr[r].z * 4u;
-                val[2 * r + 1] = __fmul_rn(__uint_as_float(pr[r].w), v);
-                if (q >= s && q < e) pend |= 1u << (2 * r);
-                if (q + 1 < e) pend |= 1u << (2 * r + 1);  // q + 1 >= s always (q >= sa >= s - 1)
-            }
-            smem_add_batch<2 * U>(addr, val, pend);
-            b += 2 * G * U;
-            if (b < maxspan) gather(b);
-        }
-#else
         base2 = n;
         if (base1 < n) {  // claim the batch of the pass after next
             if ((tid & 31) == 0) base2 = atomicAdd(next_entry, GPW);
@@ -753,7 +708,6 @@ __device__ __forceinline__ bool accumulate_chunk(const ExpandArgs x, int n, cons
             }
             smem_add_batch<2 * U>(addr, val, pend);
         }
-#endif
         if (first_pass) { prefetch_l2(s1, e1); first_pass = false; }
         s = s1; e = e1; s1 = s2; e1 = e2;
         base0 = base1; base1 = base2;
@@ -761,149 +715,6 @@ __device__ __forceinline__ bool accumulate_chunk(const ExpandArgs x, int n, cons
     }
     nxt.e = e_far;
     if (want_next) prefetch_l2(nxt.s, nxt.e);
-    return any;
-}
-
-// Variant with TWO segments in flight per lane group (-DSPY_TWOSEG=1; not the default until it is measured in the
-// kernel): a pass of a warp covers 2 * GPW consecutive entries, group gw gathers entries base + gw and
-// base + GPW + gw together -- 2 * U 16-byte loads per lane before the first add.  On the bare primitive
-// (profiles/microbench/overlap_bench_r01.txt) that lifts gather + add from 437 to 539 Gproducts/s on 50-pair segments.
-// Registers: the bounds of the entries to come are not replicated over the lanes of a group as above; lane role
-// r = gl & 3 holds ONE future segment's bounds (r = 0, 1: the next pass's two segments, r = 2, 3: the pass after), and
-// a pass begins by broadcasting them inside the group with shuffles.
-#ifndef SPY_TWOSEG
-#define SPY_TWOSEG 0
-#endif
-#ifndef SPY_TWOSEG_INLINE
-#define SPY_TWOSEG_INLINE __noinline__
-#endif
-template <int NT, int G>
-__device__ SPY_TWOSEG_INLINE bool accumulate_chunk_two(const ExpandArgs x, int n, const int *st_u, const float *st_v,
-                                                     unsigned accb32, const NextFirst pre, bool want_next, NextFirst &nxt,
-                                                     int *next_entry) {
-    constexpr int GROUPS = NT / G;
-    constexpr int GPW = 32 / G;        // groups per warp
-    constexpr int U = unroll_for(NT);  // 16-byte loads (2 pairs each) in flight per lane and segment
-    constexpr int REP = G / 4;         // lanes of a group with the same role
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int gl = tid & (G - 1);
-    const int gw = lane / G;
-    const int role = gl & 3, rep = gl >> 2;
-    const int gbase = lane & ~(G - 1);
-    int base0 = (tid >> 5) * 2 * GPW, base1 = base0 + 2 * GROUPS, base2;
-    bool any = false;
-    // one path for both layouts: bounds of B row u are sp0[u * stride], sp0[u * stride + 1]
-    const int *sp0 = (x.n_panels == 1) ? x.b_indptr : x.b_split + x.pn;
-    const int stride = (x.n_panels == 1) ? 1 : x.split_stride;
-    auto fetch = [&](int i, int &s_, int &e_) {
-        s_ = 0; e_ = 0;
-        if (i < n) {
-            const int *sp = sp0 + (size_t)st_u[i] * stride;
-            s_ = __ldg(sp); e_ = __ldg(sp + 1);
-        }
-    };
-    int sA, eA, sB, eB;  // the two segments being gathered (uniform over the group)
-    int fs, fe;          // this lane's future segment
-    if (pre.valid) { sA = pre.s; eA = pre.e; }
-    else fetch(base0 + gw, sA, eA);
-    fetch(base0 + GPW + gw, sB, eB);
-    fetch(base1 + (role & 1) * GPW + gw, fs, fe);  // roles 2, 3 are overwritten by the first pass's far fetch
-    auto prefetch_next = [&]() {  // roles 0 and 1 hold the next pass's bounds: pull its pairs into L2, replica j lines j, j + REP, ...
-#if SPY_PREFETCH
-        if (role < 2) {
-            const char *lo = reinterpret_cast<const char *>(x.b_pairs + fs), *hi = reinterpret_cast<const char *>(x.b_pairs + fe);
-#pragma unroll
-            for (int l = 0; l < 4; l++) {
-                const char *nb = lo + 128 * (rep + REP * l);
-                if (nb < hi) asm volatile("prefetch.global.L2 [%0];" ::"l"(nb));
-            }
-        }
-#endif
-    };
-    bool first_pass = true;
-    while (base0 < n) {  // warp-uniform
-        const int iA = base0 + gw, iB = iA + GPW;
-        const float vA = (iA < n) ? st_v[iA] : 0.f, vB = (iB < n) ? st_v[iB] : 0.f;
-        const int saA = sA & ~1, saB = sB & ~1;  // pairs are 8 bytes: an even position is 16-byte aligned
-        const int maxspan = __reduce_max_sync(0xffffffffu, max(eA - saA, eB - saB));
-        any |= (eA > sA) | (eB > sB);
-        uint4 pa[U], pb[U];
-        auto gather = [&](int b) {
-            const int qA = saA + b + 2 * gl, qB = saB + b + 2 * gl;
-#pragma unroll
-            for (int r = 0; r < U; r++)
-                if (qA + 2 * G * r < eA) pa[r] = ldg128(x.b_pairs + qA + 2 * G * r);  // the array is padded by one pair
-#pragma unroll
-            for (int r = 0; r < U; r++)
-                if (qB + 2 * G * r < eB) pb[r] = ldg128(x.b_pairs + qB + 2 * G * r);
-        };
-        auto housekeeping = [&]() {  // claim the entries of the pass after next, fetch their bounds, prefetch the next pass's pairs
-            base2 = n;
-            if (base1 < n) {
-                if (lane == 0) base2 = atomicAdd(next_entry, 2 * GPW);
-                base2 = __shfl_sync(0xffffffffu, base2, 0);
-            }
-            if (role >= 2) fetch(base2 + (role & 1) * GPW + gw, fs, fe);
-            if (!first_pass) prefetch_next();
-        };
-#if SPY_EARLY_GATHER
-        if (maxspan > 0) gather(0);  // in flight while the claim's atomic + shuffle round trip runs
-        housekeeping();
-#else
-        housekeeping();
-        if (maxspan > 0) gather(0);
-#endif
-        for (int b = 0; b < maxspan;) {
-            const int qA = saA + b + 2 * gl, qB = saB + b + 2 * gl;
-            unsigned addr[2 * U];
-            float val[2 * U];
-            unsigned pend = 0u;
-#pragma unroll
-            for (int r = 0; r < U; r++) {
-                const int q = qA + 2 * G * r;
-                addr[2 * r] = accb32 + pa[r].x * 4u;
-                val[2 * r] = __fmul_rn(__uint_as_float(pa[r].y), vA);
-                addr[2 * r + 1] = accb32 + pa[r].z * 4u;
-                val[2 * r + 1] = __fmul_rn(__uint_as_float(pa[r].w), vA);
-                if (q >= sA && q < eA) pend |= 1u << (2 * r);
-                if (q + 1 < eA) pend |= 1u << (2 * r + 1);
-            }
-            smem_add_batch<2 * U>(addr, val, pend);
-            pend = 0u;
-#pragma unroll
-            for (int r = 0; r < U; r++) {
-                const int q = qB + 2 * G * r;
-                addr[2 * r] = accb32 + pb[r].x * 4u;
-                val[2 * r] = __fmul_rn(__uint_as_float(pb[r].y), vB);
-                addr[2 * r + 1] = accb32 + pb[r].z * 4u;
-                val[2 * r + 1] = __fmul_rn(__uint_as_float(pb[r].w), vB);
-                if (q >= sB && q < eB) pend |= 1u << (2 * r);
-                if (q + 1 < eB) pend |= 1u << (2 * r + 1);
-            }
-            smem_add_batch<2 * U>(addr, val, pend);
-            b += 2 * G * U;
-            if (b < maxspan) gather(b);
-        }
-        if (first_pass) { prefetch_next(); first_pass = false; }
-        // next pass: its bounds come from the role 0 / 1 lanes of the group; those lanes take over what roles 2 / 3 hold
-        sA = __shfl_sync(0xffffffffu, fs, gbase); eA = __shfl_sync(0xffffffffu, fe, gbase);
-        sB = __shfl_sync(0xffffffffu, fs, gbase + 1); eB = __shfl_sync(0xffffffffu, fe, gbase + 1);
-        fs = __shfl_down_sync(0xffffffffu, fs, 2, 4); fe = __shfl_down_sync(0xffffffffu, fe, 2, 4);
-        base0 = base1; base1 = base2;
-    }
-    // the first entry's segment in the NEXT panel [this panel's end, next split point): loaded here, consumed after the drain
-    nxt.s = 0; nxt.e = 0; nxt.valid = want_next;
-    const int i_first = (tid >> 5) * 2 * GPW + gw;
-    if (want_next && i_first < n) {
-        const int *sp = sp0 + (size_t)st_u[i_first] * stride;
-        nxt.s = __ldg(sp + 1); nxt.e = __ldg(sp + 2);
-    }
-#if SPY_PREFETCH
-    if (want_next) {
-        const char *nb = reinterpret_cast<const char *>(x.b_pairs + nxt.s) + 128 * gl;
-        if (nb < reinterpret_cast<const char *>(x.b_pairs + nxt.e)) asm volatile("prefetch.global.L2 [%0];" ::"l"(nb));
-    }
-#endif
     return any;
 }
 
@@ -974,7 +785,7 @@ knn_flat_kernel(const __grid_constant__ KnnDev p) {
             if (tid < e - b) { u_n = __ldg(p.a_indices + b + tid); v_n = __ldg(p.a_data + b + tid); }
         }
     };
-    constexpr int kFirstClaim = (SPY_TWOSEG ? 4 : 2) * (NT / G);  // entries covered by the warps' two fixed passes
+    constexpr int kFirstClaim = 2 * (NT / G);  // entries covered by the warps' two fixed passes
     if (tid == 0) { claim_next(); s_entry[0] = kFirstClaim; s_entry[1] = kFirstClaim; }
     __syncthreads();
     load_next_entries();
@@ -1025,13 +836,8 @@ knn_flat_kernel(const __grid_constant__ KnnDev p) {
                 const bool first = c0 == a0;  // the cross-panel prefetch covers the first chunk of the row
                 NextFirst none = {0, 0, false}, got = none;
                 if (tid == 0) s_entry[(calls + 1) & 1] = kFirstClaim;  // last used by call `calls - 1`: two barriers ago
-#if SPY_TWOSEG
-                any |= accumulate_chunk_two<NT, G>(x, n, st_u, st_v, accb32, first ? pre : none,
-                                                   first && pn + 1 < p.n_panels, got, &s_entry[calls & 1]);
-#else
                 any |= accumulate_chunk<NT, G>(x, n, st_u, st_v, accb32, first ? pre : none,
                                                first && pn + 1 < p.n_panels, got, &s_entry[calls & 1]);
-#endif
                 calls++;
                 if (first) pre = got;
             }
