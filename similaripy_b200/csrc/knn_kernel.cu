@@ -26,6 +26,8 @@
 //   * ties are resolved deterministically: larger value first, then smaller column id.
 #include "knn_kernel.cuh"
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 #include <vector>
 
 namespace spy {
@@ -283,6 +285,35 @@ int spy_knn_topk_dev(const spy_knn_args *args, void *scratch, int64_t scratch_by
     }
     knn_kernel_t kern = pick_kernel(pl.threads, kind, pl.cand_smem, pl.group);
     SPY_CUDA_OK(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
+    // Experiment switch (off unless SPY_L2_PERSIST=<MB> is set; to be measured): keep the split table -- one random
+    // 32-byte sector per (entry, panel), re-read by every target row that contains the entry -- resident in L2
+    // against the 1.6 GB stream of pairs, through a per-launch access-policy window.
+    static const long persist_mb = [] { const char *e = getenv("SPY_L2_PERSIST"); return e ? atol(e) : 0L; }();
+    const void *table = (pl.n_panels > 1) ? (const void *)a.b_split : (const void *)a.b_indptr;
+    if (persist_mb > 0 && table != nullptr) {
+        cudaDeviceProp prop;
+        SPY_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+        const size_t carve = std::min((size_t)persist_mb << 20, (size_t)prop.persistingL2CacheMaxSize);
+        const size_t bytes = (pl.n_panels > 1) ? (size_t)a.b_rows * a.split_stride * 4 : ((size_t)a.b_rows + 1) * 4;
+        const size_t window = std::min(bytes, (size_t)prop.accessPolicyMaxWindowSize);
+        if (carve > 0 && window > 0) {
+            SPY_CUDA_OK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve));
+            cudaLaunchAttribute attr;
+            attr.id = cudaLaunchAttributeAccessPolicyWindow;
+            attr.val.accessPolicyWindow.base_ptr = const_cast<void *>(table);
+            attr.val.accessPolicyWindow.num_bytes = window;
+            attr.val.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)window);
+            attr.val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr.val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof(cfg));
+            cfg.gridDim = dim3(grid); cfg.blockDim = dim3(pl.threads); cfg.dynamicSmemBytes = pl.smem_bytes; cfg.stream = st;
+            cfg.attrs = &attr; cfg.numAttrs = 1;
+            SPY_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, d));
+            count_launch();
+            return SPY_OK;
+        }
+    }
     kern<<<grid, pl.threads, pl.smem_bytes, st>>>(d);
     SPY_LAUNCH_OK();
     return SPY_OK;
