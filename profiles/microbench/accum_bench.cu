@@ -2,7 +2,8 @@
 // Streams (col,val) products from HBM and accumulates into a per-CTA table.
 // Variants: 0 stream only, 1 smem float atomicAdd (CAS loop), 2 racy LDS/FADD/STS (upper bound, wrong),
 // 3 smem native int atomicAdd, 4 global RED.ADD.F32 into an L2-resident table,
-// 5 warp-private table, 8-lane sub-steps (conflict free, no atomics), 6 warp-private full-warp racy-free (one B row per warp instr).
+// 5 warp-private table, 8-lane sub-steps (conflict free, no atomics), 6 warp-private full-warp racy-free (one B row per warp instr),
+// 14-16 exact fixed-point accumulation on native integer adds (two 32-bit limbs / one 64-bit add / one 32-bit add).
 #include <cstdio>
 #include <cstdlib>
 #include <cstdint>
@@ -76,6 +77,16 @@ __global__ void __launch_bounds__(1024) bench(const int* __restrict__ cols, cons
                 unsigned a = sbase + (ci[j] % (W / 2)) * 8;
                 asm volatile("red.shared.add.s32 [%0], %1;" :: "r"(a), "r"(lo) : "memory");
                 asm volatile("red.shared.add.s32 [%0], %1;" :: "r"(a + 4), "r"(hi) : "memory");
+            }
+            else if (MODE == 15) {  // exact fixed point in ONE 64-bit integer add per product (8-byte slots): SASS is ATOMS.CAST.SPIN.64, a CAS loop again -- 64-bit integer adds are not native in shared memory
+                const long long q = __float2ll_rn(vi[j] * 1099511627776.0f);  // stand-in for product * 2^40
+                unsigned a = sbase + (ci[j] % (W / 2)) * 8;
+                asm volatile("red.shared.add.u64 [%0], %1;" :: "r"(a), "l"(q) : "memory");
+            }
+            else if (MODE == 16) {  // the same on 32 bits (4-byte slots): what a 32-bit fixed-point grid would cost
+                const int q = __float2int_rn(vi[j] * 1048576.0f);
+                unsigned a = sbase + ci[j] * 4;
+                asm volatile("red.shared.add.s32 [%0], %1;" :: "r"(a), "r"(q) : "memory");
             }
             else if (MODE == 12) { unsigned a = sbase + ((ci[j] & ~31) | lane) * 4; asm volatile("red.shared.add.f32 [%0], %1;" :: "r"(a), "f"(vi[j]) : "memory"); }
         }
@@ -152,6 +163,8 @@ int main() {
         run<12>("red.shared.add.f32, distinct banks", thr, cps, W, cols, vals, N, gacc, out, nsm);
         run<13>("swap-carry add, distinct banks", thr, cps, W, cols, vals, N, gacc, out, nsm);
         run<14>("fixed point, 2 native int adds (8 B slots)", thr, cps, W, cols, vals, N, gacc, out, nsm);
+        run<15>("fixed point, one 64-bit int add (8 B slots)", thr, cps, W, cols, vals, N, gacc, out, nsm);
+        run<16>("fixed point, one 32-bit int add + F2I", thr, cps, W, cols, vals, N, gacc, out, nsm);
         if (W == 49152) { run<1>("smem float atomicAdd (CAS)", 512, 1, W, cols, vals, N, gacc, out, nsm); run<1>("smem float atomicAdd (CAS)", 256, 1, W, cols, vals, N, gacc, out, nsm); }
         else { run<1>("smem float atomicAdd (CAS)", 1024, 2, W, cols, vals, N, gacc, out, nsm); run<1>("smem float atomicAdd (CAS)", 256, 2, W, cols, vals, N, gacc, out, nsm);}
     }
