@@ -16,7 +16,13 @@ __global__ void __launch_bounds__(1024, 1) gather(const uint2 *__restrict__ pair
     float acc = 0.f;
     for (int it = 0; it < segs_per_group; it++) {
         const long s = (long)(hash32(gid * 7919u + it) % (unsigned)(n_pairs - len - 64));
-        if (PF) {  // next segment into L2, lane l takes line l
+        if (PF < 0) {  // next segment into L2 by ONE bulk prefetch of exactly its bytes (cp.async.bulk.prefetch.L2)
+            const long s2 = (long)(hash32(gid * 7919u + it - PF) % (unsigned)(n_pairs - len - 64));
+            if (gl == 0) {
+                const unsigned bytes = (unsigned)(((s2 + len - (s2 & ~1L)) * 8 + 15) & ~15L);
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pairs + (s2 & ~1L)), "r"(bytes));
+            }
+        } else if (PF) {  // next segment into L2, lane l takes line l
             const long s2 = (long)(hash32(gid * 7919u + it + PF) % (unsigned)(n_pairs - len - 64));
             const char *nb = reinterpret_cast<const char *>(pairs + s2) + 128 * gl;
             if (nb < reinterpret_cast<const char *>(pairs + s2 + len)) asm volatile("prefetch.global.L2 [%0];" ::"l"(nb));
@@ -63,6 +69,8 @@ int main() {
         run<8, 2, 0>("G=8 U=2 (kernel's shape), no prefetch", pairs, n_pairs, len, out);
         run<8, 2, 1>("G=8 U=2, L2 prefetch 1 segment ahead", pairs, n_pairs, len, out);
         run<8, 2, 2>("G=8 U=2, L2 prefetch 2 segments ahead", pairs, n_pairs, len, out);
+        run<8, 2, -1>("G=8 U=2, bulk L2 prefetch 1 segment ahead", pairs, n_pairs, len, out);
+        run<8, 2, -2>("G=8 U=2, bulk L2 prefetch 2 segments ahead", pairs, n_pairs, len, out);
         run<8, 4, 0>("G=8 U=4, no prefetch", pairs, n_pairs, len, out);
         run<8, 4, 2>("G=8 U=4, L2 prefetch 2 ahead", pairs, n_pairs, len, out);
         run<16, 2, 2>("G=16 U=2, L2 prefetch 2 ahead", pairs, n_pairs, len, out);

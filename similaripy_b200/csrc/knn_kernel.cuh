@@ -663,7 +663,15 @@ __device__ __forceinline__ bool accumulate_chunk(const ExpandArgs x, int n, cons
         }
     };
     auto prefetch_l2 = [&](int s_, int e_) {  // lane l pulls line l of the segment (G lines cover G * 16 pairs)
-#if SPY_PREFETCH
+#if SPY_PREFETCH == 2
+        // experiment (to be measured): one bulk prefetch of exactly the segment's bytes per group instead of whole
+        // 128-byte lines -- a 400-byte segment at a random offset drags in ~100 bytes it never uses with line prefetches
+        if (gl == 0 && e_ > s_) {
+            const uint2 *a = x.b_pairs + (s_ & ~1);
+            const unsigned bytes = (unsigned)(((e_ - (s_ & ~1)) * 8 + 15) & ~15);
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(bytes));
+        }
+#elif SPY_PREFETCH
         const char *nb = reinterpret_cast<const char *>(x.b_pairs + s_) + 128 * gl;
         if (nb < reinterpret_cast<const char *>(x.b_pairs + e_)) asm volatile("prefetch.global.L2 [%0];" ::"l"(nb));
 #endif
