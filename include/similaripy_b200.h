@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SPY_ABI_VERSION 4
+#define SPY_ABI_VERSION 5
 
 typedef enum {
     SPY_OK = 0,
@@ -126,7 +126,24 @@ typedef struct spy_knn_args {
     int64_t b_nnz;              /* stored entries of B (b_indptr[b_rows]); 0 = unknown: only used to
                                  * size `group` from the mean segment length                      */
     int32_t group;              /* lanes streaming one B-row segment together: 4, 8, 16 or 32      */
+    /* kernel generation: 0 = let spy_knn_plan choose, SPY_ENGINE_FLAT = knn_flat_kernel (expansion and drain
+     * alternate; every configuration), SPY_ENGINE_STREAM = knn_stream_kernel (cp.async ring, the panel is
+     * snapshotted into tensor memory and drained concurrently; needs the three tables below) */
+    int32_t engine;
+    const int32_t *b_chunk_indptr; /* [b_rows + 1] first 16-byte chunk of every row of B in b_chunks          */
+    const void *b_chunks;       /* B as chunks of two (column, value) pairs, rows padded to whole chunks
+                                 * (spy_knn_pad_chunks_dev)                                                  */
+    const int64_t *toff;        /* [n_targets + 1] exclusive scan of the target rows' lengths               */
+    int64_t n_entries;          /* toff[n_targets]: stored entries of A in the target rows                    */
+    const void *aexp;           /* [n_panels][n_entries] (first chunk, end chunk) of every (entry, panel):
+                                 * spy_knn_build_aexp_dev                                                     */
 } spy_knn_args;
+
+#define SPY_ENGINE_AUTO 0
+#define SPY_ENGINE_FLAT 1
+#define SPY_ENGINE_STREAM 2
+/* what SPY_ENGINE_AUTO resolves to when the configuration is covered by both */
+#define SPY_ENGINE_DEFAULT SPY_ENGINE_FLAT
 
 /* Choose panel_width / n_panels / split_stride / threads / group for a problem (device < 0: plan with B200
  * defaults without touching the CUDA runtime).  Fills the plan fields of *args. */
@@ -147,6 +164,22 @@ int spy_knn_build_split_dev(int32_t b_rows, const int32_t *b_indptr, const int32
  * (the kernel may read one pair past the end; its content is ignored). */
 int spy_knn_pack_pairs_dev(int64_t nnz, const int32_t *b_indices, const float *b_data, void *pairs_out,
                            void *stream);
+
+/* ---- tables of the stream engine (SPY_ENGINE_STREAM), built once per call on the device ----------------
+ * counts[u] = chunks of row u of B = ceil(nnz(B[u,:]) / 2); the caller scans them into chunk_indptr
+ * (spy_exclusive_scan_i32_dev) */
+int spy_knn_chunk_counts_dev(int32_t b_rows, const int32_t *b_indptr, int32_t *counts, void *stream);
+/* chunks_out[chunk_indptr[u] + c] = pairs 2c, 2c+1 of row u as (column, value bits, column, value bits); an odd row
+ * ends with the filler pair (0xffffffff, 0), which no panel accepts.  chunks_out holds chunk_indptr[b_rows] * 16 bytes. */
+int spy_knn_pad_chunks_dev(int32_t b_rows, const int32_t *b_indptr, const int32_t *b_indices, const float *b_data,
+                           const int32_t *chunk_indptr, void *chunks_out, void *stream);
+/* len[i] = stored entries of target row i; the caller scans them into toff (spy_exclusive_scan_i64_dev) */
+int spy_knn_row_lengths_dev(int32_t n_targets, const int32_t *targets, const int32_t *a_indptr, int32_t *len, void *stream);
+/* aexp[p * n_entries + toff[i] + j] = chunk range of the part of B[u,:] (u = j-th entry of target row i) that falls
+ * into panel p.  Replaces the per-(target row, block, B row) std::lower_bound of the blocked path
+ * (s_plus.h:381-394) by one coalesced table per call.  Uses targets, a_*, b_indptr, b_chunk_indptr, b_split /
+ * split_stride / n_panels (b_split may be NULL when n_panels == 1), toff, n_entries of *args; writes args->aexp. */
+int spy_knn_build_aexp_dev(const spy_knn_args *args, void *stream);
 
 /* The hot path.  Replaces s_plus::compute_similarities_parallel<int,float>
  * (s_plus.h:265-453).  Device pointers; scratch is spy_knn_scratch_bytes() bytes. */

@@ -24,7 +24,7 @@
 //     feeds a running-threshold candidate buffer; a bitonic sort compacts it to the best k
 //     whenever it fills and once at the end of the row;
 //   * ties are resolved deterministically: larger value first, then smaller column id.
-#include "knn_kernel.cuh"
+#include "knn_stream_kernel.cuh"
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -75,16 +75,66 @@ __global__ void build_split_kernel(int b_rows, const int *__restrict__ b_indptr,
 static int next_pow2(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 
 struct Plan {
-    int threads, ctas_per_sm, W, n_panels, split_stride, cap, group;
+    int threads, ctas_per_sm, W, n_panels, split_stride, cap, group, engine;
     bool cand_smem;
     size_t smem_bytes;
+    StreamPlan stream;
 };
+
+static int similarity_kind(const spy_knn_args &a, int &exact_only);
+
+// Which kernel generation runs the call: the stream engine (knn_stream_kernel) covers every configuration except
+// matrix-mode target columns, the exact-only similarities (a1 != 1 or a bayesian shrink: no division-free pre-filter)
+// and k beyond what its candidate buffer holds; those, and explicit requests, take the flat engine.
+// SPY_ENGINE=flat|stream overrides the automatic choice (kernel experiments).
+static int choose_engine(const spy_knn_args &a, int max_smem_optin, StreamPlan &sp) {
+    int exact_only = 0;
+    similarity_kind(a, exact_only);
+    const bool eligible = !exact_only && a.target_mode != SPY_SEL_MATRIX && (a.threads == 0 || a.threads == 1024) &&
+                          stream_plan(a.k, a.n_cols, a.engine == SPY_ENGINE_STREAM ? a.panel_width : 0, max_smem_optin, sp);
+    int want = a.engine;
+    if (want == SPY_ENGINE_AUTO) {
+        static const int env = [] {
+            const char *e = getenv("SPY_ENGINE");
+            if (e && !strcmp(e, "flat")) return SPY_ENGINE_FLAT;
+            if (e && !strcmp(e, "stream")) return SPY_ENGINE_STREAM;
+            return SPY_ENGINE_AUTO;
+        }();
+        want = env != SPY_ENGINE_AUTO ? env : SPY_ENGINE_DEFAULT;
+        if (want == SPY_ENGINE_STREAM && !eligible) want = SPY_ENGINE_FLAT;
+    }
+    if (want == SPY_ENGINE_STREAM && !eligible) return -1;
+    return want;
+}
 
 static int make_plan(const spy_knn_args &a, int device, Plan &pl) {
     DeviceInfo di = device_info(device);
+    if (a.engine != SPY_ENGINE_AUTO && a.engine != SPY_ENGINE_FLAT && a.engine != SPY_ENGINE_STREAM) {
+        set_error("engine must be 0 (auto), 1 (flat) or 2 (stream), got %d", a.engine);
+        return SPY_ERR_INVALID;
+    }
+    pl.engine = choose_engine(a, di.max_smem_optin, pl.stream);
+    if (pl.engine < 0) {
+        set_error("the stream engine does not cover this configuration (matrix-mode target_cols, a1 != 1, bayesian shrink, "
+                  "threads != 1024, k > 2048 or a panel_width that is not a multiple of 512)");
+        return SPY_ERR_UNSUPPORTED;
+    }
+    if (pl.engine == SPY_ENGINE_STREAM) {
+        pl.threads = KS_NT; pl.ctas_per_sm = 1; pl.cap = pl.stream.cap; pl.cand_smem = true; pl.group = 32;
+        pl.W = pl.stream.W; pl.n_panels = pl.stream.n_panels; pl.smem_bytes = pl.stream.smem_bytes;
+        int stride = pl.n_panels + 1;
+        if (stride <= 8) { int q = 1; while (q < stride) q <<= 1; stride = q; }
+        pl.split_stride = (pl.n_panels > 1) ? stride : 0;
+        return SPY_OK;
+    }
     pl.threads = a.threads ? a.threads : 1024;
-    if (pl.threads != 512 && pl.threads != 768 && pl.threads != 1024) {
-        set_error("threads must be 512, 768 or 1024 (got %d)", pl.threads);
+#ifdef SPY_WITH_768
+    const bool threads_ok = pl.threads == 512 || pl.threads == 768 || pl.threads == 1024;
+#else
+    const bool threads_ok = pl.threads == 512 || pl.threads == 1024;  // the 768-thread kernels are an experiment build
+#endif
+    if (!threads_ok) {
+        set_error("threads must be 512 or 1024 (got %d)", pl.threads);
         return SPY_ERR_INVALID;
     }
     pl.ctas_per_sm = pl.threads == 512 ? 2 : 1;  // 512 x 2 and 1024 x 1: 64 registers per thread; 768 x 1: 80
@@ -185,6 +235,7 @@ int spy_knn_plan(spy_knn_args *args, int device) {
     args->n_panels = pl.n_panels;
     args->split_stride = pl.split_stride;
     args->group = pl.group;
+    args->engine = pl.engine;
     return SPY_OK;
 }
 
@@ -192,6 +243,7 @@ int64_t spy_knn_scratch_bytes(const spy_knn_args *args, int device) {
     if (!args) return SPY_ERR_INVALID;
     Plan pl;
     if (make_plan(*args, device, pl) != SPY_OK) return SPY_ERR_INVALID;
+    if (pl.engine == SPY_ENGINE_STREAM) return stream_scratch_bytes(args->n_cols);
     int64_t bytes = 256 + block_min_bytes(args->n_cols);  // work counter (+ phase counters), per-block minima of Y
     if (!pl.cand_smem) bytes += (int64_t)grid_size(pl, std::max(args->n_targets, 1), device) * pl.cap * 8;
     return bytes;
@@ -230,8 +282,9 @@ int spy_knn_topk_dev(const spy_knn_args *args, void *scratch, int64_t scratch_by
     if (a.n_targets == 0) return SPY_OK;
     SPY_REQUIRE(a.out_cols && a.out_values, "output slab pointers are NULL");
     SPY_REQUIRE(a.panel_width > 0 && a.n_panels > 0 && a.threads > 0, "launch plan missing: call spy_knn_plan first");
-    SPY_REQUIRE(a.b_pairs != nullptr, "b_pairs is NULL: pack B with spy_knn_pack_pairs_dev first");
-    SPY_REQUIRE(a.n_panels == 1 || a.b_split != nullptr, "n_panels > 1 needs b_split (spy_knn_build_split_dev)");
+    SPY_REQUIRE(a.engine == SPY_ENGINE_FLAT || a.engine == SPY_ENGINE_STREAM, "launch plan missing: call spy_knn_plan first");
+    SPY_REQUIRE(a.engine == SPY_ENGINE_STREAM || a.b_pairs != nullptr, "b_pairs is NULL: pack B with spy_knn_pack_pairs_dev first");
+    SPY_REQUIRE(a.engine == SPY_ENGINE_STREAM || a.n_panels == 1 || a.b_split != nullptr, "n_panels > 1 needs b_split (spy_knn_build_split_dev)");
     SPY_REQUIRE((long long)a.panel_width * a.n_panels >= a.n_cols, "panels do not cover n_cols");
     SPY_REQUIRE(a.filter_mode != SPY_SEL_MATRIX || (a.filter_indptr && a.filter_indices), "filter matrix is NULL");
     SPY_REQUIRE(a.target_mode != SPY_SEL_MATRIX || (a.target_indptr && a.target_indices), "target matrix is NULL");
@@ -245,6 +298,12 @@ int spy_knn_topk_dev(const spy_knn_args *args, void *scratch, int64_t scratch_by
     int rc = make_plan(a, device, pl);
     if (rc != SPY_OK) return rc;
     const int grid = grid_size(pl, a.n_targets, device);
+    if (pl.engine == SPY_ENGINE_STREAM) {
+        SPY_REQUIRE(pl.W == a.panel_width && pl.n_panels == a.n_panels, "plan fields were changed after spy_knn_plan");
+        int exact_only = 0;
+        const int kind = similarity_kind(a, exact_only);
+        return stream_launch(a, pl.stream, kind, exact_only, grid, scratch, scratch_bytes, as_stream(stream));
+    }
     const int64_t bm_bytes = block_min_bytes(a.n_cols);
     int64_t need = 256 + bm_bytes + (pl.cand_smem ? 0 : (int64_t)grid * pl.cap * 8);
     SPY_REQUIRE(scratch != nullptr && scratch_bytes >= need, "scratch too small: need %lld bytes", (long long)need);
@@ -378,21 +437,50 @@ int spy_knn_topk_host(const spy_knn_args *host_args, int device) {
     a.threads = host_args->threads;
     a.group = host_args->group;
     a.b_nnz = b_nnz;
+    a.engine = host_args->engine;
     rc = spy_knn_plan(&a, device);
     if (rc != SPY_OK) { cleanup(); return rc; }
-    {
-        void *d_pairs = nullptr;
-        if (!dev_alloc(&d_pairs, ((size_t)std::max(b_nnz, 1) + 1) * 8)) { cleanup(); return SPY_ERR_NOMEM; }
-        rc = spy_knn_pack_pairs_dev(b_nnz, a.b_indices, a.b_data, d_pairs, nullptr);
-        if (rc != SPY_OK) { cleanup(); return rc; }
-        a.b_pairs = d_pairs;
-    }
     if (a.n_panels > 1) {
+        // the panel split points need ascending columns inside every row of B; the reference accepts unsorted rows on
+        // its unblocked path (s_plus.h:418-438), so sort the device copy rather than require it of the caller
+        rc = spy_csr_sort_rows_dev(a.b_rows, a.b_indptr, (int32_t *)a.b_indices, (float *)a.b_data, nullptr);
+        if (rc != SPY_OK) { cleanup(); return rc; }
         if (!dev_alloc(&d_split, (size_t)a.b_rows * a.split_stride * 4)) { cleanup(); return SPY_ERR_NOMEM; }
         rc = spy_knn_build_split_dev(a.b_rows, a.b_indptr, a.b_indices, a.panel_width, a.n_panels, a.split_stride,
                                      (int32_t *)d_split, nullptr);
         if (rc != SPY_OK) { cleanup(); return rc; }
         a.b_split = (const int32_t *)d_split;
+    }
+    if (a.engine == SPY_ENGINE_STREAM) {
+        // the stream engine's tables: B as padded 16-byte chunks, the chunk range of every (entry, panel)
+        void *d_cnt = nullptr, *d_cptr = nullptr, *d_tmp = nullptr, *d_chunks = nullptr, *d_len = nullptr, *d_toff = nullptr, *d_aexp = nullptr;
+        const int64_t n_scan = std::max<int64_t>(std::max(a.b_rows, a.n_targets), 1);
+        if (!dev_alloc(&d_cnt, (size_t)n_scan * 4) || !dev_alloc(&d_cptr, ((size_t)a.b_rows + 1) * 4) ||
+            !dev_alloc(&d_tmp, (size_t)spy_scan_tmp_bytes(n_scan)) || !dev_alloc(&d_toff, ((size_t)a.n_targets + 1) * 8)) { cleanup(); return SPY_ERR_NOMEM; }
+        d_len = d_cnt;
+        rc = spy_knn_chunk_counts_dev(a.b_rows, a.b_indptr, (int32_t *)d_cnt, nullptr);
+        if (rc == SPY_OK) rc = spy_exclusive_scan_i32_dev(a.b_rows, (const int32_t *)d_cnt, (int32_t *)d_cptr, d_tmp, nullptr);
+        int32_t n_chunks = 0;
+        if (rc == SPY_OK && cudaMemcpy(&n_chunks, (int32_t *)d_cptr + a.b_rows, 4, cudaMemcpyDeviceToHost) != cudaSuccess) rc = SPY_ERR_CUDA;
+        if (rc != SPY_OK) { cleanup(); return rc; }
+        if (!dev_alloc(&d_chunks, ((size_t)std::max(n_chunks, 1)) * 16)) { cleanup(); return SPY_ERR_NOMEM; }
+        rc = spy_knn_pad_chunks_dev(a.b_rows, a.b_indptr, a.b_indices, a.b_data, (const int32_t *)d_cptr, d_chunks, nullptr);
+        if (rc == SPY_OK) rc = spy_knn_row_lengths_dev(a.n_targets, a.targets, a.a_indptr, (int32_t *)d_len, nullptr);
+        if (rc == SPY_OK) rc = spy_exclusive_scan_i64_dev(a.n_targets, (const int32_t *)d_len, (int64_t *)d_toff, d_tmp, nullptr);
+        int64_t n_entries = 0;
+        if (rc == SPY_OK && cudaMemcpy(&n_entries, (int64_t *)d_toff + a.n_targets, 8, cudaMemcpyDeviceToHost) != cudaSuccess) rc = SPY_ERR_CUDA;
+        if (rc != SPY_OK) { cleanup(); return rc; }
+        if (!dev_alloc(&d_aexp, (size_t)std::max<int64_t>(n_entries, 1) * a.n_panels * 8)) { cleanup(); return SPY_ERR_NOMEM; }
+        a.b_chunk_indptr = (const int32_t *)d_cptr; a.b_chunks = d_chunks; a.toff = (const int64_t *)d_toff;
+        a.n_entries = n_entries; a.aexp = d_aexp;
+        rc = spy_knn_build_aexp_dev(&a, nullptr);
+        if (rc != SPY_OK) { cleanup(); return rc; }
+    } else {
+        void *d_pairs = nullptr;
+        if (!dev_alloc(&d_pairs, ((size_t)std::max(b_nnz, 1) + 1) * 8)) { cleanup(); return SPY_ERR_NOMEM; }
+        rc = spy_knn_pack_pairs_dev(b_nnz, a.b_indices, a.b_data, d_pairs, nullptr);
+        if (rc != SPY_OK) { cleanup(); return rc; }
+        a.b_pairs = d_pairs;
     }
     int64_t sb = spy_knn_scratch_bytes(&a, device);
     if (sb < 0 || !dev_alloc(&d_scratch, (size_t)sb)) { cleanup(); return SPY_ERR_NOMEM; }

@@ -1,0 +1,229 @@
+// knn_stream.cu -- host side of the stream engine (knn_stream_kernel.cuh): the per-call tables it reads
+// (B as padded 16-byte chunks, the chunk range of every (entry of a target row, panel)), planning and launch.
+#include "knn_stream_kernel.cuh"
+#include <algorithm>
+
+namespace spy {
+
+// counts[u] = ceil(nnz(B[u,:]) / 2)
+__global__ void chunk_counts_kernel(int b_rows, const int *__restrict__ b_indptr, int *__restrict__ counts) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u < b_rows) counts[u] = (b_indptr[u + 1] - b_indptr[u] + 1) >> 1;
+}
+
+// one warp per row of B: chunk c of the row = its pairs 2c and 2c + 1 (filler (0xffffffff, 0) after an odd row)
+__global__ void pad_chunks_kernel(int b_rows, const int *__restrict__ b_indptr, const int *__restrict__ b_indices,
+                                  const float *__restrict__ b_data, const int *__restrict__ chunk_indptr,
+                                  uint4 *__restrict__ chunks) {
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long u = warp0; u < b_rows; u += n_warps) {
+        const int s = b_indptr[u], e = b_indptr[u + 1], c0 = chunk_indptr[u];
+        const int n = (e - s + 1) >> 1;
+        for (int c = lane; c < n; c += 32) {
+            const int q = s + 2 * c;
+            uint4 v;
+            v.x = (unsigned)b_indices[q];
+            v.y = __float_as_uint(b_data[q]);
+            v.z = 0xffffffffu;
+            v.w = 0u;
+            if (q + 1 < e) { v.z = (unsigned)b_indices[q + 1]; v.w = __float_as_uint(b_data[q + 1]); }
+            chunks[c0 + c] = v;
+        }
+    }
+}
+
+__global__ void row_lengths_kernel(int n_targets, const int *__restrict__ targets, const int *__restrict__ a_indptr,
+                                   int *__restrict__ len) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_targets) {
+        const int t = targets[i];
+        len[i] = a_indptr[t + 1] - a_indptr[t];
+    }
+}
+
+// one warp per target row: lane j of a step owns one entry (u = its column) and writes the chunk range of B[u,:]
+// inside every panel -- for a fixed panel the 32 lanes write 256 consecutive bytes
+__global__ void build_aexp_kernel(int n_targets, const int *__restrict__ targets, const int *__restrict__ a_indptr,
+                                  const int *__restrict__ a_indices, const int *__restrict__ b_indptr,
+                                  const int *__restrict__ chunk_indptr, const int *__restrict__ split, int split_stride,
+                                  int n_panels, const long long *__restrict__ toff, long long E, uint2 *__restrict__ aexp) {
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long i = warp0; i < n_targets; i += n_warps) {
+        const int t = targets[i];
+        const int a0 = a_indptr[t], len = a_indptr[t + 1] - a0;
+        const long long tq0 = toff[i];
+        for (int j = lane; j < len; j += 32) {
+            const int u = a_indices[a0 + j];
+            const int bp0 = b_indptr[u], c0 = chunk_indptr[u];
+            if (n_panels == 1) {
+                const int e = b_indptr[u + 1];
+                aexp[tq0 + j] = make_uint2((unsigned)c0, (unsigned)(c0 + ((e - bp0 + 1) >> 1)));
+            } else {
+                const int *sp = split + (size_t)u * split_stride;
+                int s = sp[0];
+                for (int p = 0; p < n_panels; p++) {
+                    const int e = sp[p + 1];
+                    const unsigned cb = (unsigned)(c0 + ((s - bp0) >> 1));
+                    const unsigned ce = e > s ? (unsigned)(c0 + ((e - bp0 + 1) >> 1)) : cb;
+                    aexp[(long long)p * E + tq0 + j] = make_uint2(cb, ce);
+                    s = e;
+                }
+            }
+        }
+    }
+}
+
+// out[b] = min of y over columns [128 b, 128 b + 128): the drain's coarse bound (one warp per block)
+__global__ void block_min128_kernel(int n, const float *__restrict__ y, float *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int blk = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
+    if (blk * 128 >= n) return;
+    float m = __int_as_float(0x7f800000);
+    for (int i = blk * 128 + lane; i < min(n, blk * 128 + 128); i += 32) m = fminf(m, y[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) out[blk] = m;
+}
+
+static int next_pow2_i(int x) { int p = 1; while (p < x) p <<= 1; return p; }
+
+bool stream_plan(int k, int n_cols, int panel_width, int max_smem_optin, StreamPlan &sp) {
+    sp.cap = std::max(1024, next_pow2_i(2 * std::max(k, 1)));
+    if (sp.cap > 4096) return false;
+    const size_t fixed = ks_fixed_bytes(sp.cap);
+    const size_t budget = (size_t)max_smem_optin - 1024;  // static shared memory of the kernel (barriers, messages) + slack
+    if (budget <= fixed + 512 * 4) return false;
+    int w_max = (int)((budget - fixed) / 4 / 512) * 512;
+    w_max = std::min(w_max, 65536);  // 128 lanes x 512 columns of tensor memory
+    n_cols = std::max(n_cols, 1);
+    int W = panel_width;
+    if (W <= 0) {
+        const int P = ceil_div(n_cols, w_max);
+        W = ceil_div(ceil_div(n_cols, P), 512) * 512;
+    } else if (W % 512 != 0 || W > w_max) return false;
+    sp.W = W;
+    sp.n_panels = ceil_div(n_cols, W);
+    sp.smem_bytes = (size_t)W * 4 + fixed;
+    return true;
+}
+
+static int64_t bm_bytes(int n_cols) { return (((int64_t)(std::max(n_cols, 1) + 127) / 128) * 4 + 255) / 256 * 256; }
+int64_t stream_scratch_bytes(int n_cols) { return 256 + 3 * bm_bytes(n_cols); }
+
+template <int KIND>
+static knn_stream_kernel_t stream_kernel() { return (knn_stream_kernel_t)knn_stream_kernel<KIND>; }
+
+int stream_launch(const spy_knn_args &a, const StreamPlan &sp, int kind, int exact_only, int grid, void *scratch,
+                  int64_t scratch_bytes, cudaStream_t st) {
+    SPY_REQUIRE(a.b_chunks && a.b_chunk_indptr && a.toff, "stream engine: b_chunks / b_chunk_indptr / toff missing");
+    SPY_REQUIRE(a.n_entries == 0 || a.aexp, "stream engine: aexp missing (spy_knn_build_aexp_dev)");
+    SPY_REQUIRE(a.target_mode != SPY_SEL_MATRIX && !exact_only, "stream engine does not cover this configuration");
+    SPY_REQUIRE(scratch != nullptr && scratch_bytes >= stream_scratch_bytes(a.n_cols), "scratch too small");
+    KnnStreamDev p;
+    KnnDev &d = p.q;
+    d.n_targets = a.n_targets; d.targets = a.targets; d.row_order = a.row_order;
+    d.a_indptr = a.a_indptr; d.a_indices = a.a_indices; d.a_data = a.a_data;
+    d.b_indptr = a.b_indptr; d.b_indices = a.b_indices; d.b_data = a.b_data;
+    d.b_pairs = nullptr; d.b_split = nullptr; d.split_stride = 0;
+    d.n_panels = sp.n_panels; d.W = sp.W; d.n_cols = a.n_cols;
+    d.Xt = a.Xtversky; d.Yt = a.Ytversky; d.Xc = a.Xcosine; d.Yc = a.Ycosine; d.Xd = a.Xdepop; d.Yd = a.Ydepop;
+    d.y_block_min = nullptr;
+    d.a1 = a.a1; d.l1 = a.l1; d.l2 = a.l2; d.l3 = a.l3; d.t1 = a.t1; d.t2 = a.t2;
+    d.stab = a.stabilized_shrink; d.bayes = a.bayesian_shrink; d.thr = a.threshold;
+    d.has_den = (a.l1 != 0.f || a.l2 != 0.f || a.l3 != 0.f || a.stabilized_shrink != 0.f || a.bayesian_shrink != 0.f) ? 1 : 0;
+    d.exact_only = exact_only;
+    d.k = a.k; d.cap = sp.cap; d.group = 0;
+    d.filter_mode = a.filter_mode; d.f_indptr = a.filter_indptr; d.f_indices = a.filter_indices;
+    d.target_mode = a.target_mode; d.t_indptr = a.target_indptr; d.t_indices = a.target_indices;
+    d.out_rows = a.out_rows; d.out_cols = a.out_cols; d.out_vals = a.out_values; d.out_counts = a.out_counts;
+    unsigned char *sc = reinterpret_cast<unsigned char *>(scratch);
+    d.work_counter = reinterpret_cast<int *>(sc);
+    d.phase = nullptr; d.cand_global = nullptr;
+    p.err = reinterpret_cast<int *>(sc + 64);
+    p.toff = reinterpret_cast<const long long *>(a.toff);
+    p.E = a.n_entries;
+    p.aexp = reinterpret_cast<const uint2 *>(a.aexp);
+    p.chunks = reinterpret_cast<const uint4 *>(a.b_chunks);
+    SPY_CUDA_OK(cudaMemsetAsync(scratch, 0, 256, st));
+    // per-128-column minima of the Y vectors in use: the drain's coarse bound
+    const int64_t bmb = bm_bytes(a.n_cols);
+    const int blocks = (std::max(a.n_cols, 1) + 127) / 128;
+    p.ymin_t = p.ymin_c = p.ymin_d = nullptr;
+    const float *src[3] = {a.l1 != 0.f ? a.Ytversky : nullptr, a.l2 != 0.f ? a.Ycosine : nullptr, a.l3 != 0.f ? a.Ydepop : nullptr};
+    const float **dst[3] = {&p.ymin_t, &p.ymin_c, &p.ymin_d};
+    for (int i = 0; i < 3; i++) {
+        if (src[i] == nullptr || a.n_cols <= 0) continue;
+        float *bm = reinterpret_cast<float *>(sc + 256 + i * bmb);
+        block_min128_kernel<<<(blocks * 32 + 255) / 256, 256, 0, st>>>(a.n_cols, src[i], bm);
+        SPY_LAUNCH_OK();
+        *dst[i] = bm;
+    }
+    knn_stream_kernel_t kern;
+    switch (kind) {
+    case KIND_RAW: kern = stream_kernel<KIND_RAW>(); break;
+    case KIND_T: kern = stream_kernel<KIND_T>(); break;
+    case KIND_C: kern = stream_kernel<KIND_C>(); break;
+    case KIND_D: kern = stream_kernel<KIND_D>(); break;
+    default: kern = stream_kernel<KIND_GEN>(); break;
+    }
+    SPY_CUDA_OK(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.smem_bytes));
+    kern<<<grid, KS_NT, sp.smem_bytes, st>>>(p);
+    SPY_LAUNCH_OK();
+    return SPY_OK;
+}
+
+}  // namespace spy
+
+using namespace spy;
+
+extern "C" {
+
+int spy_knn_chunk_counts_dev(int32_t b_rows, const int32_t *b_indptr, int32_t *counts, void *stream) {
+    if (b_rows <= 0) return SPY_OK;
+    SPY_REQUIRE(b_indptr && counts, "chunk_counts: NULL pointer");
+    chunk_counts_kernel<<<(b_rows + 255) / 256, 256, 0, as_stream(stream)>>>(b_rows, b_indptr, counts);
+    SPY_LAUNCH_OK();
+    return SPY_OK;
+}
+
+int spy_knn_pad_chunks_dev(int32_t b_rows, const int32_t *b_indptr, const int32_t *b_indices, const float *b_data,
+                           const int32_t *chunk_indptr, void *chunks_out, void *stream) {
+    if (b_rows <= 0) return SPY_OK;
+    SPY_REQUIRE(b_indptr && chunk_indptr && chunks_out, "pad_chunks: NULL pointer");
+    const long long warps = std::min<long long>(b_rows, (long long)kB200SmCount * 64);
+    pad_chunks_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, as_stream(stream)>>>(
+        b_rows, b_indptr, b_indices, b_data, chunk_indptr, reinterpret_cast<uint4 *>(chunks_out));
+    SPY_LAUNCH_OK();
+    return SPY_OK;
+}
+
+int spy_knn_row_lengths_dev(int32_t n_targets, const int32_t *targets, const int32_t *a_indptr, int32_t *len, void *stream) {
+    if (n_targets <= 0) return SPY_OK;
+    SPY_REQUIRE(targets && a_indptr && len, "row_lengths: NULL pointer");
+    row_lengths_kernel<<<(n_targets + 255) / 256, 256, 0, as_stream(stream)>>>(n_targets, targets, a_indptr, len);
+    SPY_LAUNCH_OK();
+    return SPY_OK;
+}
+
+int spy_knn_build_aexp_dev(const spy_knn_args *args, void *stream) {
+    SPY_REQUIRE(args != nullptr, "args is NULL");
+    const spy_knn_args &a = *args;
+    if (a.n_targets <= 0 || a.n_entries <= 0) return SPY_OK;
+    SPY_REQUIRE(a.n_panels >= 1, "build_aexp: launch plan missing (spy_knn_plan)");
+    SPY_REQUIRE(a.targets && a.a_indptr && a.a_indices && a.b_indptr && a.b_chunk_indptr && a.toff && a.aexp,
+                "build_aexp: NULL pointer");
+    SPY_REQUIRE(a.n_panels == 1 || (a.b_split && a.split_stride >= a.n_panels + 1), "build_aexp: n_panels > 1 needs b_split");
+    const long long warps = std::min<long long>(a.n_targets, (long long)kB200SmCount * 64);
+    build_aexp_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, as_stream(stream)>>>(
+        a.n_targets, a.targets, a.a_indptr, a.a_indices, a.b_indptr, a.b_chunk_indptr, a.b_split, a.split_stride, a.n_panels,
+        reinterpret_cast<const long long *>(a.toff), a.n_entries,
+        reinterpret_cast<uint2 *>(const_cast<void *>(a.aexp)));
+    SPY_LAUNCH_OK();
+    return SPY_OK;
+}
+
+}  // extern "C"
