@@ -4,24 +4,31 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--scale F]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (N=1): BASELINE.json configs[1] -- item-item ``cosine(URM.T, k=100)`` on a BM25-normalised
-synthetic URM of 1M users x 200k items, density 1e-3 (per-row Binomial nnz, unique uniform
-sorted columns, float32 values, seed 2).  One "step" = one complete similarity call over all 200k target
-rows: transpose, norm vectors, panel split points, the fused expand/accumulate/similarity/top-k kernel and
-the CSR assembly of the result.
+Workload: BASELINE.json configs[1] -- item-item ``cosine(URM.T, k=100)`` on a BM25-normalised synthetic URM of
+1M users x 200k items, density 1e-3 (SURVEY.md 8d generator, seed 2; the same bits in both arms, see gen_urm_*).
+One "step" = ONE complete similarity call over all 200k target rows: transposition / norm vectors / kernel tables
+(reused from the DeviceMatrix handle after the first call), the fused expand + accumulate + similarity + top-k
+kernel and the CSR assembly of the result.
 
   value  rows/s with the inputs already resident in HBM (DeviceMatrix in, DeviceMatrix out);
   e2e    rows/s through the public drop-in call ``similaripy_b200.cosine(scipy_matrix, ...)`` with HOST
          buffers (pinned): the H2D copy of the CSR and the D2H copy of the result are inside the timed region;
+         `e2e.pageable` is the same call on ordinary (pageable) numpy buffers, `e2e.int64_indices` on a scipy
+         matrix with 64-bit index arrays;
   roofline  algorithmic bytes of the hot kernel / its CUDA-event duration against MEASURED_PEAKS.json hbm_gbs;
   cpu_baseline  the compiled, unmodified reference (oracle/_ref, OpenMP, all host cores) on a bounded sample
-         of the same target rows, extrapolated to the full job (see ``sample``).
+         of the same target rows, extrapolated to the full job (see ``sample``);
+  configs   BASELINE.json configs[2..4] (s_plus 500k x 500k, rp3beta 2M x 500k, dot_product 5M x 200k with
+         filter_cols) at full operand size on a seeded sample of their target rows: rows/s, out-nnz/s, roofline;
+  normalizers  l1 / l2 / tfidf / bm25 / bm25plus on the configs[1] URM: GB/s and fraction of the HBM peak.
 
-N>1 (weak scaling): target rows shard across ranks with no data-path collective; B (=URM) is replicated;
-rank r owns its own 200k-row shard A_r (rank 0's is URM.T itself, rank r>0's is a fresh draw of the same
-shape, i.e. 200k further items scored against the same catalogue).  value = all ranks' rows / max-over-ranks time.
+N>1 is STRONG scaling of the same call (north_star): under ``sharded.shard_rows(gather=True)`` the 200k
+target rows are cut into work-balanced contiguous ranges, B is replicated, every rank runs the kernel on its range
+and writes into its slice of the gather buffer, one NCCL all-gather per slab array reassembles the full result on
+every rank -- all inside the timed region.  value = 200k rows / max-over-ranks time.
 
-``--impl reference`` times the reference's own CPU implementation (same metric / config) on the host cores.
+``--impl reference`` times the reference's own CPU implementation (same metric / config) on ALL host cores; it
+imports nothing of similaripy_b200.
 """
 from __future__ import annotations
 
@@ -51,27 +58,75 @@ def log(*a):
 
 
 # ------------------------------------------------------------------------------------------------
-# synthetic data (generated on the GPU: scipy.sparse.random is far too slow at 2e8 nnz)
+# synthetic data: the SAME bits from numpy on the host (reference arm) and from torch on the device (GPU arm)
 # ------------------------------------------------------------------------------------------------
+# SURVEY 8d's generator -- per-row nnz ~ Binomial(n_cols, density), uniform distinct ascending columns, float32
+# values -- with a counter-based hash (splitmix64) in place of a sequential RNG stream, so that the reference arm
+# (numpy, no GPU, no import of the product) and the GPU arm (torch, scipy.sparse.random is far too slow at 2e8 nnz)
+# build bit-identical matrices.  The per-row counts come from np.random.default_rng(seed).binomial on the host in
+# both arms (n_rows draws).
+_C0, _C1, _C2 = 0x9E3779B97F4A7C15, 0xBF58476D1CE4E5B9, 0x94D049BB133111EB
+
+
+def _s64(c):  # 64-bit constant as a signed python int (torch int64)
+    return c - (1 << 64) if c >= (1 << 63) else c
+
+
+def _mix_np(x):
+    x = x + np.uint64(_C0)
+    x = (x ^ (x >> np.uint64(30))) * np.uint64(_C1)
+    x = (x ^ (x >> np.uint64(27))) * np.uint64(_C2)
+    return x ^ (x >> np.uint64(31))
+
+
+def _mix_t(x):  # int64 tensor; logical right shifts emulated by masking the sign extension
+    x = x + _s64(_C0)
+    x = (x ^ ((x >> 30) & ((1 << 34) - 1))) * _s64(_C1)
+    x = (x ^ ((x >> 27) & ((1 << 37) - 1))) * _s64(_C2)
+    return x ^ ((x >> 31) & ((1 << 33) - 1))
+
+
+def row_counts(n_rows, n_cols, density, seed):
+    return np.random.default_rng(seed).binomial(n_cols, density, size=n_rows).astype(np.int64)
+
+
+def gen_urm_host(n_rows, n_cols, density, seed):
+    """scipy csr_array (int32 indices, float32 data in (0, 1]) -- numpy only."""
+    cnt = row_counts(n_rows, n_cols, density, seed)
+    rows = np.repeat(np.arange(n_rows, dtype=np.uint64), cnt)
+    with np.errstate(over="ignore"):
+        z = _mix_np(np.arange(rows.shape[0], dtype=np.uint64) + np.uint64(seed) * np.uint64(_C2))
+        key = np.unique(rows * np.uint64(n_cols) + (z >> np.uint64(11)) % np.uint64(n_cols))
+        del rows, z
+        r = key // np.uint64(n_cols)
+        indices = (key - r * np.uint64(n_cols)).astype(np.int32)
+        z = _mix_np(key ^ (np.uint64(seed) * np.uint64(_C1)))
+    data = (1.0 - ((z >> np.uint64(40)) & np.uint64(0xFFFFFF)).astype(np.float32) * np.float32(2.0 ** -24)).astype(np.float32)
+    indptr = np.zeros(n_rows + 1, dtype=np.int64)
+    np.cumsum(np.bincount(r.astype(np.int64), minlength=n_rows), out=indptr[1:])
+    m = sp.csr_array((data, indices, indptr.astype(np.int32)), shape=(n_rows, n_cols))
+    m.has_sorted_indices = True
+    return m
+
+
 def gen_urm_device(n_rows, n_cols, density, seed, device):
-    """CSR (indptr i32, indices i32, data f32) on the device: per-row nnz ~ Binomial(n_cols, density),
-    columns uniform without replacement (duplicates removed), ascending; values in (0, 1]."""
+    """The same matrix as gen_urm_host as device tensors (indptr i32, indices i32, data f32)."""
     import torch
-    g = torch.Generator(device=device)
-    g.manual_seed(seed)
-    cnt = torch.binomial(torch.full((n_rows,), float(n_cols), device=device),
-                         torch.full((n_rows,), float(density), device=device), generator=g).to(torch.int64)
+    cnt = torch.from_numpy(row_counts(n_rows, n_cols, density, seed)).to(device)
     rows = torch.repeat_interleave(torch.arange(n_rows, device=device, dtype=torch.int64), cnt)
-    cols = torch.randint(0, n_cols, (rows.numel(),), device=device, dtype=torch.int64, generator=g)
-    key = torch.unique(rows * n_cols + cols, sorted=True)
-    del rows, cols
+    seed_a = _s64((seed * _C2) & ((1 << 64) - 1))
+    seed_b = _s64((seed * _C1) & ((1 << 64) - 1))
+    z = _mix_t(torch.arange(rows.numel(), device=device, dtype=torch.int64) + seed_a)
+    key = torch.unique(rows * n_cols + ((z >> 11) & ((1 << 53) - 1)) % n_cols, sorted=True)
+    del rows, z
     r = torch.div(key, n_cols, rounding_mode="floor")
     indices = (key - r * n_cols).to(torch.int32)
+    z = _mix_t(key ^ seed_b)
     del key
+    data = 1.0 - ((z >> 40) & 0xFFFFFF).to(torch.float32) * (2.0 ** -24)
+    del z
     indptr = torch.zeros(n_rows + 1, dtype=torch.int64, device=device)
     indptr[1:] = torch.cumsum(torch.bincount(r, minlength=n_rows), 0)
-    del r
-    data = (1.0 - torch.rand(indices.numel(), device=device, dtype=torch.float32, generator=g))
     return indptr.to(torch.int32), indices, data
 
 
@@ -142,19 +197,29 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # the reference on the host cores (oracle/_ref = the compiled, unmodified reference)
 # ------------------------------------------------------------------------------------------------
+def host_threads():
+    """All the host threads this process may use (torchrun exports OMP_NUM_THREADS=1, which must not throttle the
+    reference: its thread count is passed explicitly, `#pragma omp parallel num_threads(n)`, s_plus.h:313)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def reference_callable():
-    """(fn, kind): fn(matrix1, target_rows) -> csr result through the reference's own s_plus driver."""
+    """(fn, kind, threads): fn(matrix1, target_rows) -> csr result through the reference's own s_plus driver."""
     from oracle import ref_api
+    threads = host_threads()
     if ref_api.available():
         from oracle import ref_api as impl
-        kind, threads = "reference", impl.num_threads()
+        kind = "reference"
     else:
         from oracle import oracle as impl
-        kind, threads = "port", impl.max_threads()
+        kind = "port"
 
     def fn(matrix1, target_rows):
         return impl.similarity("cosine", matrix1, None, k=K_NEIGHBOURS, target_rows=target_rows,
-                               format_output="csr", verbose=False, num_threads=0)
+                               format_output="csr", verbose=False, num_threads=threads)
     return fn, kind, threads
 
 
@@ -216,55 +281,187 @@ def dist_setup(n_gpus):
 
 
 def host_csr_views(indptr, indices, data, shape):
-    """scipy csr_array over pinned host buffers without copying."""
+    """scipy csr_array over existing host buffers without copying."""
     m = sp.csr_array((data, indices, indptr), shape=shape, copy=False)
     assert np.shares_memory(m.data, data) and np.shares_memory(m.indices, indices)
     m.has_sorted_indices = True
     return m
 
 
+def load_peak():
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    except Exception:
+        return 6650.0, "fallback 6650 GB/s (B200_PROFILING.md)"
+
+
+def device_matrix(n_rows, n_cols, density, seed, dev):
+    import similaripy_b200 as sim
+    from similaripy_b200 import _engine
+    ip, ix, dv = gen_urm_device(n_rows, n_cols, density, seed, dev)
+    return sim.DeviceMatrix(_engine.DeviceCSR(n_rows, n_cols, ip, ix, dv, sorted_rows=True), False)
+
+
+def job_products(job):
+    """(scalar products, stored entries of A) of the job's target rows -- SURVEY 8d's P and nnz_A."""
+    import torch
+    A, B = job.A, job.B
+    b_len = (B.indptr[1:] - B.indptr[:-1]).to(torch.int64)
+    cum = torch.zeros(A.nnz + 1, dtype=torch.int64, device=A.indptr.device)
+    torch.cumsum(b_len[A.indices.long()], 0, out=cum[1:])
+    t = job.targets.long()
+    lo, hi = A.indptr[t].long(), A.indptr[t + 1].long()
+    return int((cum[hi] - cum[lo]).sum().item()), int((hi - lo).sum().item())
+
+
+def kernel_line(name, job, n_rows_total, peak, reps=3):
+    """Hot-kernel numbers of one prepared job (tables built, operands resident): median of `reps` launches."""
+    import torch
+    products, nnz_a = job_products(job)
+    ms = []
+    for _ in range(reps + 1):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(job.ctx.stream); job.run(); e1.record(job.ctx.stream); torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    k_ms = float(np.median(ms[1:]))
+    out_nnz = int(job.out_counts.sum().item())
+    alg = 8 * job.n_targets + 16 * nnz_a + 8 * products + 8 * out_nnz
+    return {"config": name, "target_rows_sampled": job.n_targets, "target_rows_total": n_rows_total, "k": job.k,
+            "rows_per_s": round(job.n_targets / k_ms * 1e3, 1), "out_nnz_per_s": round(out_nnz / k_ms * 1e3, 1),
+            "kernel_ms": round(k_ms, 3), "products": products, "gproducts_per_s": round(products / k_ms / 1e6, 1),
+            "roofline": {"bound": "hbm", "achieved": round(alg / k_ms / 1e6, 1), "peak": peak, "unit": "GB/s",
+                         "frac": round(alg / k_ms / 1e6 / peak, 4), "algorithmic_bytes": alg},
+            "full_job_estimate_s": round(n_rows_total / (job.n_targets / k_ms * 1e3), 2),
+            "plan": {"engine": int(job.args.engine), "n_panels": int(job.args.n_panels),
+                     "panel_width": int(job.args.panel_width), "group": int(job.args.group)},
+            "sample": f"hot kernel on {job.n_targets} seeded random target rows of {n_rows_total}; operands at full size",
+            "cpu_baseline": None}
+
+
+def sample_rows(n, m, seed):
+    return np.sort(np.random.default_rng(seed).choice(n, size=min(m, n), replace=False)).astype(np.int32)
+
+
+def other_configs(local, peak, scale):
+    """BASELINE.json configs[2..4] on one GPU: full-size synthetic operands, a seeded sample of the target rows."""
+    import torch
+    import similaripy_b200 as sim
+    from similaripy_b200 import _engine
+    dev = torch.device("cuda", local)
+    sc = lambda n: max(64, int(n * scale))
+    out = []
+
+    def guarded(name, fn):
+        try:
+            out.append(fn())
+        except Exception as exc:  # one configuration must not take the line down
+            out.append({"config": name, "error": repr(exc)[:300]})
+        torch.cuda.empty_cache()
+
+    def cfg2():  # s_plus(X, k=200, shrink=10), public defaults l1=l2=0.5, t1=t2=1, c1=c2=0.5 (similarity.py:509-515)
+        x = device_matrix(sc(500_000), sc(500_000), 2e-3, 3, dev)
+        job = _engine.prepare_job(x, None, k=200, target_rows=sample_rows(sc(500_000), 20_000, 3), verbose=False, device=local,
+                                  l1=0.5, l2=0.5, t1=1.0, t2=1.0, c1=0.5, c2=0.5, stabilized_shrink=10.0)
+        return kernel_line("configs[2]: s_plus k=200 shrink=10, 500k x 500k d=2e-3", job, sc(500_000), peak)
+
+    def cfg3():  # rp3beta(URM.T, alpha=1, beta=0.6, k=100): item-item (benchmark.py:161), similarity.py:477-503
+        urm = device_matrix(sc(2_000_000), sc(500_000), 5e-4, 4, dev)
+        pop = _engine.axis_sum(urm, 0)
+        job = _engine.prepare_job(sim.normalize(urm.T, norm="l1", axis=1), sim.normalize(urm, norm="l1", axis=1), k=100,
+                                  target_rows=sample_rows(sc(500_000), 60_000, 4), verbose=False, device=local,
+                                  weight_depop_matrix2=pop, p2=0.6, l3=1.0)
+        return kernel_line("configs[3]: rp3beta beta=0.6 k=100 item-item, URM 2M x 500k d=5e-4", job, sc(500_000), peak)
+
+    def cfg4():  # dot_product(URM, S.T, k=100, filter_cols=URM): S with ~100 neighbours per item
+        urm = device_matrix(sc(5_000_000), sc(200_000), 1e-3, 5, dev)
+        s_t = device_matrix(sc(200_000), sc(200_000), 5e-4, 55, dev)
+        job = _engine.prepare_job(urm, s_t, k=100, target_rows=sample_rows(sc(5_000_000), 500_000, 5), filter_cols=urm,
+                                  verbose=False, device=local)
+        return kernel_line("configs[4]: dot_product URM x S.T filter_cols=URM k=100, URM 5M x 200k d=1e-3", job, sc(5_000_000), peak)
+
+    guarded("configs[2]", cfg2)
+    guarded("configs[3]", cfg3)
+    guarded("configs[4]", cfg4)
+    return out
+
+
+def normalizer_lines(urm, peak):
+    """In-place CSR normalizers on the configs[1] URM (2e8 nnz, f32 / i32): GB/s over nnz * (2 x 4 B values + 4 B index)
+    x passes and the fraction of the HBM peak."""
+    import torch
+    import similaripy_b200 as sim
+    nnz = urm.nnz
+    work = urm.stored
+    saved = work.data.clone()
+    cases = [("l1", 2, lambda m: sim.normalize(m, norm="l1", inplace=True)),
+             ("l2", 2, lambda m: sim.normalize(m, norm="l2", inplace=True)),
+             ("tfidf", 3, lambda m: sim.tfidf(m, inplace=True)),
+             ("bm25", 3, lambda m: sim.bm25(m, inplace=True)),
+             ("bm25plus", 3, lambda m: sim.bm25plus(m, inplace=True))]
+    out = []
+    for name, passes, fn in cases:
+        ms = []
+        for _ in range(4):
+            work.data.copy_(saved)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(urm); e1.record(); torch.cuda.synchronize()
+            ms.append(e0.elapsed_time(e1))
+        t = float(np.median(ms[1:]))
+        bytes_ = nnz * (2 * 4 + 4) * passes if name in ("tfidf", "bm25", "bm25plus") else nnz * 2 * 4 * passes // 2 + nnz * 0
+        gbs = bytes_ / t / 1e6
+        out.append({"normalizer": name, "ms": round(t, 3), "gnnz_per_s": round(nnz / t / 1e6, 2), "gb_per_s": round(gbs, 1),
+                    "frac": round(gbs / peak, 4), "bytes_model": f"{bytes_} B per call"})
+    work.data.copy_(saved)
+    work.invalidate()
+    return out
+
+
 def run_ours(args):
     import torch
     import similaripy_b200 as sim
-    from similaripy_b200 import _engine, _lib
+    from similaripy_b200 import _engine, _lib, sharded
 
     world, rank, local = dist_setup(args.gpus)
     dev = torch.device("cuda", local)
     n_users = max(64, int(CFG2["n_users"] * args.scale))
     n_items = max(64, int(CFG2["n_items"] * args.scale))
     density = CFG2["density"] if args.scale == 1.0 else min(0.5, CFG2["density"] / args.scale ** 0.5)
+    peak, peak_source = load_peak()
     t_setup = time.perf_counter()
 
-    # ---- inputs: URM (B, replicated on every rank) and this rank's target shard A_r -----------------------
-    indptr, indices, data = gen_urm_device(n_users, n_items, density, CFG2["seed"], dev)
-    urm = sim.DeviceMatrix(_engine.DeviceCSR(n_users, n_items, indptr, indices, data, sorted_rows=True), False)
-    urm = sim.bm25(urm, inplace=True)  # BM25-normalised, as configs[1] says; outside the timed region
-    if rank == 0:
-        m1 = urm.T  # exactly configs[1]: cosine(URM.T)
-        m2 = None
-    else:  # weak scaling: 200k further item rows scored against the same catalogue
-        ip, ix, dv = gen_urm_device(n_users, n_items, density, CFG2["seed"] + 1000 * rank, dev)
-        shard = sim.DeviceMatrix(_engine.DeviceCSR(n_users, n_items, ip, ix, dv, sorted_rows=True), False)
-        shard = sim.bm25(shard, inplace=True)
-        m1, m2 = shard.T, urm
+    # ---- inputs: every rank holds the same URM (B is replicated; SURVEY 8e) ----------------------------------
+    urm_raw = device_matrix(n_users, n_items, density, CFG2["seed"], dev)
+    normalizers = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        normalizers = normalizer_lines(urm_raw, peak)
+    urm = sim.bm25(urm_raw, inplace=True)  # BM25-normalised, as configs[1] says; outside the timed region
+    m1 = urm.T  # exactly configs[1]: cosine(URM.T)
     torch.cuda.synchronize()
     nnz = urm.nnz
     n_targets = n_items
     log(f"[bench r{rank}] URM {n_users}x{n_items} nnz={nnz} generated+bm25 in {time.perf_counter() - t_setup:.1f}s")
 
     common = dict(k=K_NEIGHBOURS, verbose=False, format_output="csr", device=local)
-    if os.environ.get("SPY_TUNING"):  # kernel experiments only, e.g. SPY_TUNING="threads=512,pairs=0"
+    if os.environ.get("SPY_TUNING"):  # kernel experiments only, e.g. SPY_TUNING="engine=1,threads=512"
         common["tuning"] = {k: int(v) for k, v in (kv.split("=") for kv in os.environ["SPY_TUNING"].split(","))}
 
-    def step_device():
-        return sim.cosine(m1, m2, on_device=True, **common)
+    def sharded_call(fn):
+        if world > 1:  # ONE call, target rows cut by work over the ranks, full result gathered on every rank
+            with sharded.shard_rows(gather=True):
+                return fn()
+        return fn()
 
-    # ---- device-resident timing ------------------------------------------------------------------------
+    def step_device():
+        return sharded_call(lambda: sim.cosine(m1, None, on_device=True, **common))
+
     def barrier():
         if world > 1:
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
+    # ---- device-resident timing ------------------------------------------------------------------------
     for _ in range(args.warmup):
         res = step_device()
     out_nnz = res.nnz
@@ -288,39 +485,36 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     elapsed_ms = ev0.elapsed_time(ev1)
     kern_ms = float(np.mean([t["start"].elapsed_time(t["end"]) for t in trace]))
-    plan = {k: trace[0][k] for k in ("n_panels", "panel_width", "threads", "group")}
+    plan = {k: trace[0][k] for k in ("engine", "n_panels", "panel_width", "threads", "group")}
+    rows_local = int(trace[0]["n_targets"])
+    kern_ms_max = kern_ms
     if world > 1:
         t = torch.tensor([elapsed_ms, kern_ms], device=dev, dtype=torch.float64)
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         elapsed_ms, kern_ms_max = float(t[0]), float(t[1])
     ms_per_step = elapsed_ms / args.steps
-    value = world * n_targets / (ms_per_step / 1e3)
+    value = n_targets / (ms_per_step / 1e3)
 
-    # ---- algorithmic bytes of the hot kernel for this rank's launch ------------------------------
-    A, B = (_engine.transpose_csr(_engine.Ctx(local), m1.stored), urm.stored)  # A = CSR of the target shard
-    b_len = (B.indptr[1:] - B.indptr[:-1]).to(torch.int64)
-    products = int(b_len[A.indices.long()].sum().item())
-    alg_bytes = 8 * n_targets + 16 * A.nnz + 8 * products + 8 * out_nnz
-    del A, b_len
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
+    # ---- algorithmic bytes of THIS rank's launch of the hot kernel ------------------------------
+    probe = sharded_call(lambda: _engine.prepare_job(m1, None, **{k: v for k, v in common.items() if k != "format_output"}))
+    products, nnz_a = job_products(probe)
+    share = probe.n_targets / max(n_targets, 1)
+    del probe
+    alg_bytes = 8 * rows_local + 16 * nnz_a + 8 * products + 8 * int(out_nnz * share)
     achieved = alg_bytes / (kern_ms / 1e3) / 1e9
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": None,
-                "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)" if peaks else "fallback 6650",
-                "kernel": "knn_flat_kernel", "kernel_ms": round(kern_ms, 3), "algorithmic_bytes": alg_bytes,
+                "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_source,
+                "kernel": "knn_stream_kernel" if plan["engine"] == 2 else "knn_flat_kernel", "kernel_ms": round(kern_ms, 3),
+                "kernel_ms_max_over_ranks": round(kern_ms_max, 3), "algorithmic_bytes": alg_bytes, "target_rows_this_rank": rows_local,
                 "products": products, "gproducts_per_s": round(products / (kern_ms / 1e3) / 1e9, 1),
-                "kernel_share_of_step": round(kern_ms / ms_per_step, 4), "plan": plan}
+                "kernel_share_of_step": round(kern_ms_max / ms_per_step, 4), "plan": plan}
     traffic_file = os.path.join(ROOT, "profiles", "knn_traffic.json")
-    if os.path.exists(traffic_file):  # dram bytes per launch from the committed ncu --set full capture
+    if os.path.exists(traffic_file) and world == 1:  # dram bytes per launch from the committed ncu --set full capture
         try:
             tj = json.load(open(traffic_file))
-            if tj.get("workload_nnz") == nnz:
+            if tj.get("kernel") == roofline["kernel"] and abs(tj.get("workload_nnz", 0) - nnz) <= 0.001 * nnz:
                 roofline["traffic"] = tj.get("dram_bytes_per_launch")
+                roofline["traffic_source"] = tj.get("source")
         except Exception:
             pass
 
@@ -328,39 +522,47 @@ def run_ours(args):
     e2e = None
     cpu = None
     if not args.no_e2e:
-        src = m1.stored  # CSR of (shard) URM; matrix1 = its transpose, as a scipy CSC view -- no host conversion
+        src = urm.stored  # CSR of URM; matrix1 = its transpose, as a scipy CSC view -- no host conversion
         h = [pinned_numpy(t) for t in (src.indptr, src.indices, src.data)]
         urm_host = host_csr_views(h[0], h[1], h[2], (n_users, n_items))
-        if m2 is not None:
-            hb = [pinned_numpy(t) for t in (urm.stored.indptr, urm.stored.indices, urm.stored.data)]
-            b_host = host_csr_views(hb[0], hb[1], hb[2], (n_users, n_items))
-        else:
-            b_host = None
-        h2d = sum(x.nbytes for x in h) + (sum(x.nbytes for x in hb) if b_host is not None else 0)
+        h2d = sum(x.nbytes for x in h)
 
-        def step_host():
-            return sim.cosine(urm_host.T, b_host, **common)
+        def timed_host(matrix, steps):
+            call = lambda: sharded_call(lambda: sim.cosine(matrix.T, None, **common))
+            for _ in range(max(1, min(args.warmup, 2))):
+                r = call()
+            barrier()
+            t0 = time.perf_counter()
+            ev0.record()
+            for _ in range(steps):
+                r = call()
+            ev1.record()
+            barrier()
+            wall = time.perf_counter() - t0
+            ms = max(ev0.elapsed_time(ev1), wall * 1e3) / steps
+            if world > 1:
+                t = torch.tensor([ms], device=dev, dtype=torch.float64)
+                torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+                ms = float(t[0])
+            return ms, r
 
-        for _ in range(max(1, min(args.warmup, 2))):
-            r = step_host()
-        d2h = r.data.nbytes + r.indices.nbytes + r.indptr.nbytes
         e_steps = max(1, min(args.steps, 5))
-        barrier()
-        t0 = time.perf_counter()
-        ev0.record()
-        for _ in range(e_steps):
-            r = step_host()
-        ev1.record()
-        barrier()
-        wall = time.perf_counter() - t0
-        e_ms = max(ev0.elapsed_time(ev1), wall * 1e3) / e_steps
-        if world > 1:
-            t = torch.tensor([e_ms], device=dev, dtype=torch.float64)
-            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-            e_ms = float(t[0])
-        e2e = {"value": round(world * n_targets / (e_ms / 1e3), 1), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+        e_ms, r = timed_host(urm_host, e_steps)
+        d2h = r.data.nbytes + r.indices.nbytes + r.indptr.nbytes
+        e2e = {"value": round(n_targets / (e_ms / 1e3), 1), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": round(e_ms, 2), "steps": e_steps,
-               "call": "similaripy_b200.cosine(scipy csc (pinned), k=100, format_output='csr') -> scipy csr"}
+               "call": "similaripy_b200.cosine(scipy csc (pinned), k=100, format_output='csr') -> scipy csr"
+                       + (" under sharded.shard_rows(gather=True) on every rank" if world > 1 else "")}
+        if world == 1 and not args.no_extras:
+            # the same call on what a user normally holds: pageable numpy buffers, and 64-bit index arrays
+            pg = host_csr_views(h[0].copy(), h[1].copy(), h[2].copy(), (n_users, n_items))
+            ms_pg, _ = timed_host(pg, max(1, min(e_steps, 2)))
+            e2e["pageable"] = {"value": round(n_targets / (ms_pg / 1e3), 1), "ms_per_step": round(ms_pg, 2)}
+            i64 = host_csr_views(h[0].astype(np.int64), h[1].astype(np.int64), pg.data, (n_users, n_items))
+            ms_64, _ = timed_host(i64, max(1, min(e_steps, 2)))
+            e2e["int64_indices"] = {"value": round(n_targets / (ms_64 / 1e3), 1), "ms_per_step": round(ms_64, 2),
+                                    "h2d_bytes_per_step": int(sum(x.nbytes for x in (i64.indptr, i64.indices, i64.data)))}
+            del pg, i64
 
         # ---- CPU baseline (rank 0, N=1 only) ------------------------------------------------------------------
         if world == 1 and not args.no_cpu:
@@ -379,20 +581,28 @@ def run_ours(args):
                                   f"= {st['full_job_s']:.1f}s; scipy tocsr of URM.T ({t_tocsr:.1f}s) excluded")}
             except Exception as exc:  # the baseline must never take the GPU numbers down with it
                 cpu = {"value": None, "unit": UNIT, "error": repr(exc)[:200]}
+        del urm_host, h
+
+    configs = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        del urm, urm_raw, m1
+        torch.cuda.empty_cache()
+        configs = other_configs(local, peak, args.scale)
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "configs[1]: cosine item-item on BM25-normalised URM, k=100",
                        "n_users": n_users, "n_items": n_items, "density": density, "nnz": nnz, "k": K_NEIGHBOURS,
-                       "target_rows_per_gpu": n_targets, "out_nnz_per_gpu": out_nnz,
-                       "out_nnz_per_s": round(world * out_nnz / (ms_per_step / 1e3), 1),
+                       "target_rows": n_targets, "out_nnz": out_nnz,
+                       "out_nnz_per_s": round(out_nnz / (ms_per_step / 1e3), 1),
                        "l2_policy": "inputs (1.6 GB CSR per operand) far larger than the 126 MB L2; no flush needed",
-                       "parallelism": f"target rows sharded over {world} GPU(s), B replicated, no collective"},
+                       "parallelism": (f"ONE call: target rows cut by work over {world} GPU(s), B replicated, "
+                                       + ("NCCL all-gather of the output slab inside the timed region" if world > 1 else "no collective"))},
             "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "gpu_launches": int(launches),
-            "clocks": clocks,
+            "clocks": clocks, "configs": configs, "normalizers": normalizers,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -400,43 +610,23 @@ def run_ours(args):
 
 
 def run_reference(args):
-    """The reference's own CPU implementation on the host cores (rank 0 only)."""
+    """The reference's own CPU implementation on ALL host cores (rank 0 only); nothing of similaripy_b200 is imported."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     n_users = max(64, int(CFG2["n_users"] * args.scale))
     n_items = max(64, int(CFG2["n_items"] * args.scale))
     density = CFG2["density"] if args.scale == 1.0 else min(0.5, CFG2["density"] / args.scale ** 0.5)
-    urm = None
-    try:  # same generator as the GPU arm when a GPU is there (bit-identical workload), numpy otherwise
-        import torch
-        if torch.cuda.is_available():
-            import similaripy_b200 as sim
-            from similaripy_b200 import _engine
-            dev = torch.device("cuda", 0)
-            indptr, indices, data = gen_urm_device(n_users, n_items, density, CFG2["seed"], dev)
-            m = sim.DeviceMatrix(_engine.DeviceCSR(n_users, n_items, indptr, indices, data, sorted_rows=True), False)
-            m = sim.bm25(m, inplace=True)
-            s = m.stored
-            urm = sp.csr_array((s.data.cpu().numpy(), s.indices.cpu().numpy(), s.indptr.cpu().numpy()),
-                               shape=(n_users, n_items))
-            del m, s, indptr, indices, data
-            torch.cuda.empty_cache()
-    except Exception as exc:
-        log(f"[bench reference] GPU generator unavailable ({exc!r}); generating on the host")
-    if urm is None:
+    from oracle import ref_api
+    t0 = time.perf_counter()
+    urm = gen_urm_host(n_users, n_items, density, CFG2["seed"])  # bit-identical to the GPU arm's matrix
+    if ref_api.available():
+        urm = ref_api.bm25(urm)
+    else:
         from oracle import oracle
-        rng = np.random.default_rng(CFG2["seed"])
-        cnt = rng.binomial(n_items, density, size=n_users)
-        rows = np.repeat(np.arange(n_users, dtype=np.int64), cnt)
-        key = np.unique(rows * n_items + rng.integers(0, n_items, size=rows.shape[0]))
-        r = key // n_items
-        indptr = np.zeros(n_users + 1, dtype=np.int64)
-        np.cumsum(np.bincount(r, minlength=n_users), out=indptr[1:])
-        urm = sp.csr_array(((1.0 - rng.random(key.shape[0], dtype=np.float32)), (key - r * n_items).astype(np.int32),
-                            indptr.astype(np.int32)), shape=(n_users, n_items))
         urm = oracle.bm25(urm)
     a_csr = urm.T.tocsr()
+    log(f"[bench reference] URM {n_users}x{n_items} nnz={urm.nnz} generated + bm25 + tocsr on the host in {time.perf_counter() - t0:.1f}s")
     rt = ReferenceTimer(a_csr, n_items)
     t_fixed, t_row = rt.calibrate()
     total_steps = args.steps + args.warmup
@@ -454,7 +644,7 @@ def run_reference(args):
               f"{np.mean([s['t_row'] for s in stats]) * 1e3:.3f} ms/row = {full:.1f}s")
     line = {"impl": "reference", "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(wall * 1e3, 1), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "configs[1]: cosine item-item on BM25-normalised URM, k=100", "n_users": n_users,
                        "n_items": n_items, "density": density, "nnz": int(urm.nnz), "k": K_NEIGHBOURS},
             "cpu_baseline": {"value": round(value, 1), "unit": UNIT, "cores": rt.threads, "kind": rt.kind,
@@ -473,6 +663,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (testing only; 1.0 = configs[1])")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the configs[2..4] / normalizers / pageable-e2e lines")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work in the cpu_baseline sample")
     ap.add_argument("--ref-budget-s", type=float, default=150.0, help="wall budget of the --impl reference run")
     args = ap.parse_args()

@@ -35,6 +35,14 @@ struct Lib {
     int (*pack)(int64_t, const int32_t *, const float *, void *, void *);
     int (*topk)(const spy_knn_args *, void *, int64_t, void *);
     const char *(*last_error)(void);
+    // stream engine tables (absent in round-1 builds)
+    int (*chunk_counts)(int32_t, const int32_t *, int32_t *, void *);
+    int (*pad_chunks)(int32_t, const int32_t *, const int32_t *, const float *, const int32_t *, void *, void *);
+    int (*row_lengths)(int32_t, const int32_t *, const int32_t *, int32_t *, void *);
+    int (*build_aexp)(const spy_knn_args *, void *);
+    int64_t (*scan_tmp)(int64_t);
+    int (*scan32)(int64_t, const int32_t *, int32_t *, void *, void *);
+    int (*scan64)(int64_t, const int32_t *, int64_t *, void *, void *);
 };
 
 int main(int argc, char **argv) {
@@ -110,6 +118,8 @@ int main(int argc, char **argv) {
     std::vector<int32_t> ref_cols, ref_counts; std::vector<float> ref_vals;
     for (int li = 6; li < argc; li++) {
         Lib L;
+        int arg_engine = -1;  // "lib.so@2": run this library with engine 2 (stream); "@1": flat
+        if (char *at = strrchr(argv[li], '@')) { arg_engine = atoi(at + 1); *at = 0; }
         L.h = dlopen(argv[li], RTLD_NOW | RTLD_LOCAL);
         if (!L.h) { printf("%-44s dlopen failed: %s\n", argv[li], dlerror()); continue; }
         L.plan = (decltype(L.plan))dlsym(L.h, "spy_knn_plan");
@@ -119,18 +129,55 @@ int main(int argc, char **argv) {
         L.topk = (decltype(L.topk))dlsym(L.h, "spy_knn_topk_dev");
         L.last_error = (decltype(L.last_error))dlsym(L.h, "spy_last_error");
         if (!L.plan || !L.scratch_bytes || !L.build_split || !L.pack || !L.topk) { printf("%s: missing symbols\n", argv[li]); continue; }
+        L.chunk_counts = (decltype(L.chunk_counts))dlsym(L.h, "spy_knn_chunk_counts_dev");
+        L.pad_chunks = (decltype(L.pad_chunks))dlsym(L.h, "spy_knn_pad_chunks_dev");
+        L.row_lengths = (decltype(L.row_lengths))dlsym(L.h, "spy_knn_row_lengths_dev");
+        L.build_aexp = (decltype(L.build_aexp))dlsym(L.h, "spy_knn_build_aexp_dev");
+        L.scan_tmp = (decltype(L.scan_tmp))dlsym(L.h, "spy_scan_tmp_bytes");
+        L.scan32 = (decltype(L.scan32))dlsym(L.h, "spy_exclusive_scan_i32_dev");
+        L.scan64 = (decltype(L.scan64))dlsym(L.h, "spy_exclusive_scan_i64_dev");
         spy_knn_args a = base;
         if (const char *t = getenv("SPY_PROBE_THREADS")) a.threads = atoi(t);
         if (const char *g = getenv("SPY_PROBE_GROUP")) a.group = atoi(g);
+        if (const char *g = getenv("SPY_PROBE_ENGINE")) a.engine = atoi(g);
+        if (const char *g = getenv("SPY_PROBE_WIDTH")) a.panel_width = atoi(g);
+        if (arg_engine >= 0) a.engine = arg_engine;
         int rc = L.plan(&a, 0);
         if (rc) { printf("%s: plan failed: %s\n", argv[li], L.last_error()); continue; }
-        rc = L.pack(nnz, a.b_indices, a.b_data, d_pairs, nullptr);
-        a.b_pairs = d_pairs;
         int32_t *d_split = nullptr;
-        if (!rc && a.n_panels > 1) {
+        if (a.n_panels > 1) {
             CK(cudaMalloc(&d_split, (size_t)R * a.split_stride * 4));
             rc = L.build_split(R, a.b_indptr, a.b_indices, a.panel_width, a.n_panels, a.split_stride, d_split, nullptr);
             a.b_split = d_split;
+        }
+        void *d_cnt = nullptr, *d_cptr = nullptr, *d_tmp = nullptr, *d_chunks = nullptr, *d_toff = nullptr, *d_aexp = nullptr;
+        float prep_ms = 0.f;
+        if (!rc && a.engine == 2) {
+            if (!L.chunk_counts || !L.pad_chunks || !L.row_lengths || !L.build_aexp) { printf("%s: no stream engine\n", argv[li]); continue; }
+            cudaEvent_t p0, p1; cudaEventCreate(&p0); cudaEventCreate(&p1);
+            const int64_t n_scan = std::max(R, n_t);
+            CK(cudaMalloc(&d_cnt, (size_t)n_scan * 4)); CK(cudaMalloc(&d_cptr, ((size_t)R + 1) * 4));
+            CK(cudaMalloc(&d_tmp, (size_t)L.scan_tmp(n_scan))); CK(cudaMalloc(&d_toff, ((size_t)n_t + 1) * 8));
+            CK(cudaEventRecord(p0));
+            rc = L.chunk_counts(R, a.b_indptr, (int32_t *)d_cnt, nullptr);
+            if (!rc) rc = L.scan32(R, (const int32_t *)d_cnt, (int32_t *)d_cptr, d_tmp, nullptr);
+            int32_t n_chunks = 0;
+            CK(cudaMemcpy(&n_chunks, (int32_t *)d_cptr + R, 4, cudaMemcpyDeviceToHost));
+            CK(cudaMalloc(&d_chunks, (size_t)std::max(n_chunks, 1) * 16));
+            if (!rc) rc = L.pad_chunks(R, a.b_indptr, a.b_indices, a.b_data, (const int32_t *)d_cptr, d_chunks, nullptr);
+            if (!rc) rc = L.row_lengths(n_t, a.targets, a.a_indptr, (int32_t *)d_cnt, nullptr);
+            if (!rc) rc = L.scan64(n_t, (const int32_t *)d_cnt, (int64_t *)d_toff, d_tmp, nullptr);
+            int64_t n_entries = 0;
+            CK(cudaMemcpy(&n_entries, (int64_t *)d_toff + n_t, 8, cudaMemcpyDeviceToHost));
+            CK(cudaMalloc(&d_aexp, (size_t)std::max<int64_t>(n_entries, 1) * a.n_panels * 8));
+            a.b_chunk_indptr = (const int32_t *)d_cptr; a.b_chunks = d_chunks; a.toff = (const int64_t *)d_toff;
+            a.n_entries = n_entries; a.aexp = d_aexp;
+            if (!rc) rc = L.build_aexp(&a, nullptr);
+            CK(cudaEventRecord(p1)); CK(cudaEventSynchronize(p1));
+            cudaEventElapsedTime(&prep_ms, p0, p1);
+        } else if (!rc) {
+            rc = L.pack(nnz, a.b_indices, a.b_data, d_pairs, nullptr);
+            a.b_pairs = d_pairs;
         }
         const int64_t sb = L.scratch_bytes(&a, 0);
         void *d_scratch = nullptr;
@@ -178,10 +225,19 @@ int main(int argc, char **argv) {
                 bad_rows += bad;
             }
         }
-        printf("%-44s %8.3f ms  %7.1f Gprod/s  panels %d x %d  threads %d group %d   rows differing from the first library: %ld\n",
-               argv[li], best, products / best / 1e6, a.n_panels, a.panel_width, a.threads, a.group, bad_rows);
+        if (getenv("SPY_PROBE_PHASES") && a.engine == 2) {  // -DSPY_KS_TIMING builds: 24 cycle counters at the end of the scratch
+            unsigned long long ph[24];
+            CK(cudaMemcpy(ph, (char *)d_scratch + sb - 256, sizeof(ph), cudaMemcpyDeviceToHost));
+            const char *names[24] = {"X snapshot", "X pass body", "X end-of-pass barrier", "X snapshot", "X wait drain", "X setup+first issue", "X passes", "",
+                                     "S snapshot", "S staging", "S end-of-pass barrier", "S snapshot", "S wait drain", "S setup", "S passes", "",
+                                     "D wait snapshot", "D sweep", "D forced selections", "D evaluate/tighten", "D final select+write", "D selections", "D slot batches", ""};
+            for (int i = 0; i < 24; i++) if (names[i][0]) printf("    %-24s %12.3f Mcycles per CTA%s\n", names[i], ph[i] / 148.0 / 1e6, (i % 8 == 6 || i == 21) ? " (count, in millions)" : "");
+        }
+        printf("%-44s %8.3f ms  %7.1f Gprod/s  engine %d (tables %.2f ms) panels %d x %d  threads %d group %d   rows differing from the first library: %ld\n",
+               argv[li], best, products / best / 1e6, a.engine, prep_ms, a.n_panels, a.panel_width, a.threads, a.group, bad_rows);
         fflush(stdout);
         cudaFree(d_scratch); if (d_split) cudaFree(d_split);
+        cudaFree(d_cnt); cudaFree(d_cptr); cudaFree(d_tmp); cudaFree(d_chunks); cudaFree(d_toff); cudaFree(d_aexp);
     }
     return 0;
 }

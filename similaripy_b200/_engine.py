@@ -18,6 +18,9 @@ import scipy.sparse as sp
 from . import _lib
 from . import sharded as _sharded
 
+# Reuse prepared operands across calls on the same DeviceMatrix (SIMILARIPY_B200_CACHE=0 switches it off)
+CACHE_OPERANDS = os.environ.get("SIMILARIPY_B200_CACHE", "1") != "0"
+
 # When set to a list, every hot-kernel launch appends {start, end (CUDA events), plan...} to it (bench.py).
 KERNEL_TRACE = None
 
@@ -107,10 +110,29 @@ class DeviceCSR:
     indices: object
     data: object
     sorted_rows: bool = False
+    # Operands prepared once and reused by later calls on the same handle (s_plus.pyx:205-269 redoes all of this on
+    # every call): transposes, the row-sorted copy, squared norms / sums, the kernel's stream layouts and split
+    # tables.  Anything that overwrites `data` in place must call invalidate().
+    cache: dict = field(default_factory=dict, repr=False, compare=False)
 
     @property
     def nnz(self) -> int:
         return int(self.indices.numel())
+
+    def invalidate(self) -> None:
+        self.cache.clear()
+
+    def cached(self, key, build, partner=None):
+        """cache[key], built on first use.  `partner`: another object the value was derived from (e.g. the B
+        operand of a table stored on A); the entry only counts while it is the very same object."""
+        if not CACHE_OPERANDS:
+            return build()
+        hit = self.cache.get(key)
+        if hit is not None and hit[0] is partner:
+            return hit[1]
+        value = build()
+        self.cache[key] = (partner, value)
+        return value
 
 
 class DeviceMatrix:
@@ -190,6 +212,31 @@ def transpose_csr(ctx: Ctx, m: DeviceCSR, sort: bool = True) -> DeviceCSR:
     return DeviceCSR(m.n_cols, m.n_rows, t_indptr, t_indices, t_data, sorted_rows=bool(sort))
 
 
+def cached_transpose(ctx: Ctx, m: DeviceCSR, sort: bool = True) -> DeviceCSR:
+    """transpose_csr through the handle's cache (a row-sorted transpose also serves callers that do not need the order)."""
+    if not CACHE_OPERANDS:
+        return transpose_csr(ctx, m, sort=sort)
+    hit = m.cache.get("T_sorted")
+    if hit is None and not sort:
+        hit = m.cache.get("T")
+    if hit is not None:
+        return hit[1]
+    return m.cached("T_sorted" if sort else "T", lambda: transpose_csr(ctx, m, sort=sort))
+
+
+def sorted_rows(ctx: Ctx, m: DeviceCSR) -> DeviceCSR:
+    """m with ascending column ids inside every row (sort_indices, s_plus_utils.pyx:344,573).  The caller's buffers are
+    never permuted: an unsorted matrix is cloned, the clone sorted, and the result kept on the handle."""
+    if m.sorted_rows:
+        return m
+
+    def build():
+        c = DeviceCSR(m.n_rows, m.n_cols, m.indptr, m.indices.clone(), m.data.clone(), sorted_rows=True)
+        _lib.check(ctx.lib.spy_csr_sort_rows_dev(c.n_rows, _ptr(c.indptr), _ptr(c.indices), _ptr(c.data), ctx.sptr))
+        return c
+    return m.cached("sorted", build) if CACHE_OPERANDS else build()
+
+
 def filter_csr(ctx: Ctx, m: DeviceCSR, col_mask=None, drop_zeros=False, values=None) -> DeviceCSR:
     """Keep entries with mask[col] != 0 and/or value != 0; returns m itself when nothing is dropped."""
     torch = ctx.torch
@@ -250,11 +297,11 @@ def upload_pair(ctx: Ctx, matrix1, matrix2):
     the data crosses PCIe once and is transposed once on the GPU, whichever of CSR / CSC matrix1 is."""
     s1, t1 = upload_stored(ctx, matrix1)
     if matrix2 is None:  # A's row order is free; B is sorted later only if the plan has several panels
-        other = transpose_csr(ctx, s1, sort=False)
+        other = cached_transpose(ctx, s1, sort=False)
         return (other, s1) if t1 else (s1, other)
-    A = transpose_csr(ctx, s1, sort=False) if t1 else s1
+    A = cached_transpose(ctx, s1, sort=False) if t1 else s1
     s2, t2 = upload_stored(ctx, matrix2)
-    B = transpose_csr(ctx, s2) if t2 else s2
+    B = cached_transpose(ctx, s2) if t2 else s2
     return A, B
 
 
@@ -353,6 +400,7 @@ class KnnJob:
     shard: object = None      # sharded.ShardPlan when the target rows are split over ranks
     exchange: object = None   # sharded.SlabExchange when the full result is gathered on every rank
     targets_np: object = None  # the FULL target list on the host (sharded runs)
+    targets_key: object = None  # ("all", n) / ("range", lo, hi, n) when the target list is (a range of) all rows, else None
 
     # ---- norm vectors (s_plus.pyx:259-269) ------------------------------------------------
     def build_vectors(self, weight_depop_matrix1, weight_depop_matrix2, p1, p2, c1, c2, additive_shrink):
@@ -360,11 +408,8 @@ class KnnJob:
         A, B, P = self.A, self.B, self.params
         v = {}
         if P["l1"] != 0 or P["l2"] != 0:  # _build_squared_norms, s_plus_utils.pyx:169-201
-            sq1 = ctx.empty(A.n_rows, torch.float32)
-            _lib.check(lib.spy_csr_row_sum_dev(A.n_rows, _ptr(A.indptr), _ptr(A.data), 1, _ptr(sq1), ctx.sptr))
-            sq2 = ctx.empty(B.n_cols, torch.float32)
-            acc = ctx.empty(max(B.n_cols, 1), torch.float64)
-            _lib.check(lib.spy_csr_col_sum_dev(B.nnz, _ptr(B.indices), _ptr(B.data), 1, B.n_cols, _ptr(acc), _ptr(sq2), ctx.sptr))
+            sq1 = A.cached("row_sq", lambda: self._row_sum(A, 1))
+            sq2 = B.cached("col_sq", lambda: self._col_sum(B, 1))
         if P["l1"] != 0:
             v["Xt"], v["Yt"] = sq1, sq2
         if P["l2"] != 0:  # _build_cosine_normalization, s_plus_utils.pyx:204-228
@@ -376,6 +421,19 @@ class KnnJob:
             v["Xd"] = self._depop(weight_depop_matrix1, p1, axis=1)
             v["Yd"] = self._depop(weight_depop_matrix2, p2, axis=0)
         self.vectors = v
+
+    def _row_sum(self, m, square):
+        ctx = self.ctx
+        out = ctx.empty(m.n_rows, ctx.torch.float32)
+        _lib.check(ctx.lib.spy_csr_row_sum_dev(m.n_rows, _ptr(m.indptr), _ptr(m.data), square, _ptr(out), ctx.sptr))
+        return out
+
+    def _col_sum(self, m, square):
+        ctx = self.ctx
+        out = ctx.empty(m.n_cols, ctx.torch.float32)
+        acc = ctx.empty(max(m.n_cols, 1), ctx.torch.float64)
+        _lib.check(ctx.lib.spy_csr_col_sum_dev(m.nnz, _ptr(m.indices), _ptr(m.data), square, m.n_cols, _ptr(acc), _ptr(out), ctx.sptr))
+        return out
 
     def _depop(self, spec, p, axis):
         ctx, lib, torch = self.ctx, self.ctx.lib, self.ctx.torch
@@ -401,12 +459,7 @@ class KnnJob:
         elif spec == "none":
             out.fill_(1.0)
         elif spec == "sum":
-            s = ctx.empty(n, torch.float32)
-            if axis == 1:
-                _lib.check(lib.spy_csr_row_sum_dev(m.n_rows, _ptr(m.indptr), _ptr(m.data), 0, _ptr(s), ctx.sptr))
-            else:
-                acc = ctx.empty(max(n, 1), torch.float64)
-                _lib.check(lib.spy_csr_col_sum_dev(m.nnz, _ptr(m.indices), _ptr(m.data), 0, n, _ptr(acc), _ptr(s), ctx.sptr))
+            s = m.cached("row_sum", lambda: self._row_sum(m, 0)) if axis == 1 else m.cached("col_sum", lambda: self._col_sum(m, 0))
             _lib.check(lib.spy_pow_shift_dev(n, _ptr(s), _lib.F32, 0.0, p, _ptr(out), ctx.sptr))
         else:
             raise ValueError(f"Invalid depopularization weights: {spec}")
@@ -442,17 +495,22 @@ class KnnJob:
         `rank`.  Every rank computes the same cut from the same inputs; nothing is communicated."""
         ctx, torch = self.ctx, self.ctx.torch
         rank, world = spec.resolve()
-        if self.n_targets > 0:
-            work = ctx.empty(self.n_targets, torch.int64)
-            _lib.check(ctx.lib.spy_knn_row_work_dev(self.n_targets, _ptr(self.targets), _ptr(self.A.indptr),
-                                                    _ptr(self.A.indices), _ptr(self.B.indptr), _ptr(work), ctx.sptr))
-            work_np = work.cpu().numpy()
-        else:
-            work_np = np.zeros(0, dtype=np.int64)
-        self.shard = _sharded.ShardPlan(rank, world, _sharded.balanced_bounds(work_np, world))
+        def cut():
+            if self.n_targets > 0:
+                work = ctx.empty(self.n_targets, torch.int64)
+                _lib.check(ctx.lib.spy_knn_row_work_dev(self.n_targets, _ptr(self.targets), _ptr(self.A.indptr),
+                                                        _ptr(self.A.indices), _ptr(self.B.indptr), _ptr(work), ctx.sptr))
+                work_np = work.cpu().numpy()
+            else:
+                work_np = np.zeros(0, dtype=np.int64)
+            return _sharded.balanced_bounds(work_np, world)
+        bounds = self.A.cached(("cut", self.targets_key, world), cut, partner=self.B) if self.targets_key is not None else cut()
+        self.shard = _sharded.ShardPlan(rank, world, bounds)
         self.targets_np = targets_np
         self.targets = self.targets[self.shard.lo: self.shard.hi]
         self.n_targets = self.shard.n_local
+        if self.targets_key is not None:
+            self.targets_key = ("range", self.shard.lo, self.shard.hi, self.targets_key[1])
         if spec.gather:
             self.exchange = _sharded.SlabExchange(self.shard, self.k, torch, ctx.device)
             self.gather_group = spec.group
@@ -513,21 +571,59 @@ class KnnJob:
         a.panel_width = int(self.tuning.get("panel_width", 0))
         a.group = int(self.tuning.get("group", 0))
         a.b_nnz = B.nnz
+        eng = self.tuning.get("engine", 0)
+        a.engine = _lib.ENGINES[eng] if isinstance(eng, str) else int(eng)
         _lib.check(lib.spy_knn_plan(C.byref(a), ctx.index))
         if a.n_panels > 1:
-            if not B.sorted_rows:  # the panel split needs ascending columns inside every row of B
-                _lib.check(lib.spy_csr_sort_rows_dev(B.n_rows, _ptr(B.indptr), _ptr(B.indices), _ptr(B.data), ctx.sptr))
-                B.sorted_rows = True
-            split = ctx.empty(B.n_rows * a.split_stride, torch.int32)
-            _lib.check(lib.spy_knn_build_split_dev(B.n_rows, _ptr(B.indptr), _ptr(B.indices), a.panel_width, a.n_panels,
-                                                   a.split_stride, _ptr(split), ctx.sptr))
+            # the panel split needs ascending columns inside every row of B (a sorted CLONE when it is not: the
+            # caller's handle is never permuted)
+            B = self.B = sorted_rows(ctx, B)
+            a.b_indptr, a.b_indices, a.b_data = _ptr(B.indptr), _ptr(B.indices), _ptr(B.data)
+
+            def build_split():
+                split = ctx.empty(B.n_rows * a.split_stride, torch.int32)
+                _lib.check(lib.spy_knn_build_split_dev(B.n_rows, _ptr(B.indptr), _ptr(B.indices), a.panel_width, a.n_panels,
+                                                       a.split_stride, _ptr(split), ctx.sptr))
+                return split
+            split = B.cached(("split", int(a.panel_width), int(a.n_panels), int(a.split_stride)), build_split)
             a.b_split = _ptr(split)
             self.keep.append(split)
-        # 8-byte (column, value) stream layout of B
-        pairs = ctx.empty((max(B.nnz, 1) + 1) * 2, torch.int32)  # +1: the kernel reads 16-byte words
-        _lib.check(lib.spy_knn_pack_pairs_dev(B.nnz, _ptr(B.indices), _ptr(B.data), _ptr(pairs), ctx.sptr))
-        a.b_pairs = _ptr(pairs)
-        self.keep.append(pairs)
+        if a.engine == _lib.ENGINE_STREAM:
+            def build_chunks():  # B as 16-byte chunks of two (column, value) pairs, every row padded to whole chunks
+                cnt = ctx.empty(max(B.n_rows, 1), torch.int32)[: B.n_rows]
+                _lib.check(lib.spy_knn_chunk_counts_dev(B.n_rows, _ptr(B.indptr), _ptr(cnt), ctx.sptr))
+                chunk_indptr = ctx.scan_i32(cnt)
+                n_chunks = int(chunk_indptr[-1].item()) if B.n_rows > 0 else 0
+                chunks = ctx.empty(max(n_chunks, 1) * 4, torch.int32)
+                _lib.check(lib.spy_knn_pad_chunks_dev(B.n_rows, _ptr(B.indptr), _ptr(B.indices), _ptr(B.data),
+                                                      _ptr(chunk_indptr), _ptr(chunks), ctx.sptr))
+                return chunk_indptr, chunks
+            chunk_indptr, chunks = B.cached("chunks", build_chunks)
+            a.b_chunk_indptr, a.b_chunks = _ptr(chunk_indptr), _ptr(chunks)
+
+            def build_tables():  # chunk range of every (entry of a target row, panel)
+                rl = ctx.empty(max(self.n_targets, 1), torch.int32)[: self.n_targets]
+                _lib.check(lib.spy_knn_row_lengths_dev(self.n_targets, _ptr(self.targets), _ptr(A.indptr), _ptr(rl), ctx.sptr))
+                toff = ctx.scan_i64(rl)
+                n_entries = int(toff[-1].item()) if self.n_targets > 0 else 0
+                aexp = ctx.empty(max(n_entries, 1) * int(a.n_panels) * 2, torch.int32)
+                a.toff, a.n_entries, a.aexp = _ptr(toff), n_entries, _ptr(aexp)
+                _lib.check(lib.spy_knn_build_aexp_dev(C.byref(a), ctx.sptr))
+                return toff, n_entries, aexp
+            if self.targets_key is not None:  # all rows, or this rank's contiguous range of them: reusable
+                toff, n_entries, aexp = A.cached(("aexp", self.targets_key, int(a.panel_width), int(a.n_panels)), build_tables, partner=B)
+            else:
+                toff, n_entries, aexp = build_tables()
+            a.toff, a.n_entries, a.aexp = _ptr(toff), n_entries, _ptr(aexp)
+            self.keep += [chunk_indptr, chunks, toff, aexp]
+        else:
+            def build_pairs():  # 8-byte (column, value) stream layout of B
+                pairs = ctx.empty((max(B.nnz, 1) + 1) * 2, torch.int32)  # +1: the kernel reads 16-byte words
+                _lib.check(lib.spy_knn_pack_pairs_dev(B.nnz, _ptr(B.indices), _ptr(B.data), _ptr(pairs), ctx.sptr))
+                return pairs
+            pairs = B.cached("pairs", build_pairs)
+            a.b_pairs = _ptr(pairs)
+            self.keep.append(pairs)
         slab = self.n_targets * self.k
         if self.exchange is not None:  # the kernel writes into this rank's slice of the all-gather buffer
             self.out_cols, self.out_vals, self.out_counts = self.exchange.local()
@@ -556,7 +652,7 @@ class KnnJob:
             ev1.record(self.ctx.stream)
             trace.append(dict(start=ev0, end=ev1, n_targets=self.n_targets, k=self.k, n_panels=int(self.args.n_panels),
                               panel_width=int(self.args.panel_width), threads=int(self.args.threads),
-                              group=int(self.args.group)))
+                              group=int(self.args.group), engine=int(self.args.engine)))
 
     # ---- output (s_plus.pyx:405-424) --------------------------------------------------------------
     def assemble_device(self, format_output):
@@ -662,7 +758,8 @@ def prepare_job(matrix1, matrix2=None, weight_depop_matrix1="none", weight_depop
     params = dict(a1=f32(a1), l1=f32(l1), l2=f32(l2), l3=f32(l3), t1=f32(t1), t2=f32(t2),
                   stabilized_shrink=f32(stabilized_shrink), bayesian_shrink=f32(bayesian_shrink), threshold=f32(threshold))
     job = KnnJob(ctx=ctx, A=A, B=B, targets=ctx.h2d(targets_np), n_targets=int(targets_np.shape[0]), k=k,
-                 n_rows=n_rows, n_cols=n_cols, params=params, unique_targets=unique, tuning=dict(tuning or {}))
+                 n_rows=n_rows, n_cols=n_cols, params=params, unique_targets=unique, tuning=dict(tuning or {}),
+                 targets_key=("all", n_rows) if target_rows is None else None)
     job.build_vectors(weight_depop_matrix1, weight_depop_matrix2, f32(p1), f32(p2), f32(c1), f32(c2), f32(additive_shrink))
     job.build_selectors(filter_cols, target_cols, raw_b)
     spec = _sharded.active()
@@ -731,6 +828,7 @@ def pow_values_(m: DeviceMatrix, p: float) -> DeviceMatrix:
     ctx = Ctx(m.device)
     d = m.stored.data
     _lib.check(ctx.lib.spy_pow_shift_dev(d.numel(), _ptr(d), _lib.F32, 0.0, float(p), _ptr(d), ctx.sptr))
+    m.stored.invalidate()  # the values changed: cached transposes / norms / stream layouts are stale
     return m
 
 

@@ -38,6 +38,7 @@ class KnnArgs(C.Structure):
         ("panel_width", _i32), ("b_split", _vp), ("split_stride", _i32), ("n_panels", _i32),
         ("threads", _i32), ("b_pairs", _vp), ("row_order", _vp),
         ("b_nnz", _i64), ("group", _i32),
+        ("engine", _i32), ("b_chunk_indptr", _vp), ("b_chunks", _vp), ("toff", _vp), ("n_entries", _i64), ("aexp", _vp),
     ]
 
 
@@ -52,6 +53,10 @@ SIGNATURES = {
     "spy_knn_scratch_bytes": (_i64, [C.POINTER(KnnArgs), C.c_int]),
     "spy_knn_build_split_dev": (C.c_int, [_i32, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),
     "spy_knn_row_work_dev": (C.c_int, [_i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "spy_knn_chunk_counts_dev": (C.c_int, [_i32, _vp, _vp, _vp]),
+    "spy_knn_pad_chunks_dev": (C.c_int, [_i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "spy_knn_row_lengths_dev": (C.c_int, [_i32, _vp, _vp, _vp, _vp]),
+    "spy_knn_build_aexp_dev": (C.c_int, [C.POINTER(KnnArgs), _vp]),
     "spy_knn_topk_dev": (C.c_int, [C.POINTER(KnnArgs), _vp, _i64, _vp]),
     "spy_knn_topk_host": (C.c_int, [C.POINTER(KnnArgs), C.c_int]),
     "spy_csr_row_sum_dev": (C.c_int, [_i32, _vp, _vp, C.c_int, _vp, _vp]),
@@ -76,7 +81,9 @@ SIGNATURES = {
                                    C.c_int, C.c_int, _f64, _vp, _vp]),
 }
 
-ABI_VERSION = 4
+ABI_VERSION = 5
+ENGINE_AUTO, ENGINE_FLAT, ENGINE_STREAM = 0, 1, 2
+ENGINES = {"auto": ENGINE_AUTO, "flat": ENGINE_FLAT, "stream": ENGINE_STREAM}
 _lib = None
 
 

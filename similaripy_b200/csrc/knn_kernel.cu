@@ -116,7 +116,7 @@ static int make_plan(const spy_knn_args &a, int device, Plan &pl) {
     pl.engine = choose_engine(a, di.max_smem_optin, pl.stream);
     if (pl.engine < 0) {
         set_error("the stream engine does not cover this configuration (matrix-mode target_cols, a1 != 1, bayesian shrink, "
-                  "threads != 1024, k > 2048 or a panel_width that is not a multiple of 512)");
+                  "threads != 1024, k > 512 or a panel_width that is not a multiple of 2048)");
         return SPY_ERR_UNSUPPORTED;
     }
     if (pl.engine == SPY_ENGINE_STREAM) {

@@ -89,22 +89,20 @@ __global__ void block_min128_kernel(int n, const float *__restrict__ y, float *_
     if (lane == 0) out[blk] = m;
 }
 
-static int next_pow2_i(int x) { int p = 1; while (p < x) p <<= 1; return p; }
-
 bool stream_plan(int k, int n_cols, int panel_width, int max_smem_optin, StreamPlan &sp) {
-    sp.cap = std::max(1024, next_pow2_i(2 * std::max(k, 1)));
-    if (sp.cap > 4096) return false;
-    const size_t fixed = ks_fixed_bytes(sp.cap);
-    const size_t budget = (size_t)max_smem_optin - 1024;  // static shared memory of the kernel (barriers, messages) + slack
-    if (budget <= fixed + 512 * 4) return false;
-    int w_max = (int)((budget - fixed) / 4 / 512) * 512;
+    sp.cap = KS_CAP;
+    if (2 * std::max(k, 1) > KS_CAP) return false;  // the candidate buffer holds k kept keys plus what one sweep step adds
+    const size_t fixed = ks_fixed_bytes();
+    const size_t budget = (size_t)max_smem_optin - 1024;  // static shared memory of the kernel (barriers, descriptors) + slack
+    if (budget <= fixed + 2048 * 4) return false;
+    int w_max = (int)((budget - fixed) / 4 / 2048) * 2048;  // whole groups of four 512-column tiles
     w_max = std::min(w_max, 65536);  // 128 lanes x 512 columns of tensor memory
     n_cols = std::max(n_cols, 1);
     int W = panel_width;
     if (W <= 0) {
         const int P = ceil_div(n_cols, w_max);
-        W = ceil_div(ceil_div(n_cols, P), 512) * 512;
-    } else if (W % 512 != 0 || W > w_max) return false;
+        W = ceil_div(ceil_div(n_cols, P), 2048) * 2048;
+    } else if (W % 2048 != 0 || W > w_max) return false;
     sp.W = W;
     sp.n_panels = ceil_div(n_cols, W);
     sp.smem_bytes = (size_t)W * 4 + fixed;
@@ -112,7 +110,7 @@ bool stream_plan(int k, int n_cols, int panel_width, int max_smem_optin, StreamP
 }
 
 static int64_t bm_bytes(int n_cols) { return (((int64_t)(std::max(n_cols, 1) + 127) / 128) * 4 + 255) / 256 * 256; }
-int64_t stream_scratch_bytes(int n_cols) { return 256 + 3 * bm_bytes(n_cols); }
+int64_t stream_scratch_bytes(int n_cols) { return 256 + 3 * bm_bytes(n_cols) + 256; }
 
 template <int KIND>
 static knn_stream_kernel_t stream_kernel() { return (knn_stream_kernel_t)knn_stream_kernel<KIND>; }
@@ -142,13 +140,15 @@ int stream_launch(const spy_knn_args &a, const StreamPlan &sp, int kind, int exa
     d.out_rows = a.out_rows; d.out_cols = a.out_cols; d.out_vals = a.out_values; d.out_counts = a.out_counts;
     unsigned char *sc = reinterpret_cast<unsigned char *>(scratch);
     d.work_counter = reinterpret_cast<int *>(sc);
-    d.phase = nullptr; d.cand_global = nullptr;
+    d.phase = reinterpret_cast<u64 *>(sc + 256 + 3 * bm_bytes(a.n_cols));  // SPY_KS_TIMING builds: 24 counters
+    d.cand_global = nullptr;
     p.err = reinterpret_cast<int *>(sc + 64);
     p.toff = reinterpret_cast<const long long *>(a.toff);
     p.E = a.n_entries;
     p.aexp = reinterpret_cast<const uint2 *>(a.aexp);
     p.chunks = reinterpret_cast<const uint4 *>(a.b_chunks);
     SPY_CUDA_OK(cudaMemsetAsync(scratch, 0, 256, st));
+    SPY_CUDA_OK(cudaMemsetAsync(sc + 256 + 3 * bm_bytes(a.n_cols), 0, 256, st));
     // per-128-column minima of the Y vectors in use: the drain's coarse bound
     const int64_t bmb = bm_bytes(a.n_cols);
     const int blocks = (std::max(a.n_cols, 1) + 127) / 128;

@@ -2,23 +2,23 @@
 //
 // Replaces s_plus::compute_similarities_parallel<int,float> (reference similaripy/cython_code/s_plus.h:265-453)
 // like knn_flat_kernel (knn_kernel.cuh), whose similarity arithmetic, key order and selection rules it shares.
-// What changes is the schedule inside the CTA (one persistent CTA of 1024 threads per SM):
+// What changes is the schedule inside the CTA (one persistent CTA of 1024 threads per SM), D = KS_D_WARPS:
 //
-//   warps 5..31  EXPAND   stream B as 16-byte chunks of two (column, value) pairs with cp.async (LDGSTS) into a
+//   warps D..31  EXPAND   stream B as 16-byte chunks of two (column, value) pairs with cp.async (LDGSTS) into a
 //                         lane-private shared-memory ring -- the next batch is in flight while the current one is added
 //                         to the panel with red.shared.add.f32 (s_plus.h:358-403 / 418-438).  The chunks of a pass are
-//                         numbered through by an exclusive scan of the segments' chunk counts and cut into 27 equal
+//                         numbered through by an exclusive scan of the segments' chunk counts and cut into equal
 //                         ranges, one per warp, whatever the segment lengths: every lane of every warp has work, and
-//                         a long B row is shared by several warps;
-//   warp  4      STAGE    claims target rows from the atomic queue (`omp for schedule(dynamic)`, s_plus.h:337) and
-//                         prepares the NEXT pass while the current one is expanded: per entry of the target row the
-//                         chunk range of its B-row segment inside the panel (read coalesced from the per-call
-//                         `aexp` table -- no dependent split-point lookup on the critical path), the value of the
-//                         entry, and the scan;
-//   warps 4..31  SNAPSHOT when a panel is complete: LDS.128 -> STS.128 (reset to "untouched") -> tcgen05.st: the panel
+//                         a long B row is shared by several warps.  The same warps STAGE the next pass while the
+//                         current one runs: per entry of the target row the chunk range of its B-row segment inside
+//                         the panel (read coalesced from the per-call `aexp` table -- no dependent split-point lookup
+//                         on the critical path), the entry's value, and a per-warp scan of the chunk counts;
+//   warp  D      QUEUE    also claims target rows from the atomic queue (`omp for schedule(dynamic)`, s_plus.h:337) and
+//                         resolves the pass descriptors two passes ahead;
+//   warps D..31  SNAPSHOT when a panel is complete: LDS.128 -> STS.128 (reset to "untouched") -> tcgen05.st: the panel
 //                         moves to TENSOR MEMORY (256 KB per SM, idle in a kernel without MMAs) and the expansion of
 //                         the next panel starts at once;
-//   warps 0..3   DRAIN    read the snapshot back with tcgen05.ld (each warp its lane quarter), apply the coarse
+//   warps 0..D-1 DRAIN    read the snapshot back with tcgen05.ld (each warp its lane quarter), apply the coarse
 //                         per-128-column bound, the per-slot pre-filter, computeSimilarity (s_plus.h:129-156), the
 //                         threshold (s_plus.h:206) and keep the best k (s_plus.h:45-59, 193-215), concurrently with
 //                         the expansion.  TMEM is read-only for the drain, so an overflowing candidate buffer just
@@ -43,29 +43,46 @@ struct KnnStreamDev {
     int *err;                // set to non-zero before a trap (bounded waits)
 };
 
+#ifndef SPY_KS_D_WARPS
+#define SPY_KS_D_WARPS 4
+#endif
+#ifndef SPY_KS_U
+#define SPY_KS_U 2
+#endif
+#ifndef SPY_KS_PREFETCH
+#define SPY_KS_PREFETCH 1
+#endif
 constexpr int KS_NT = 1024;
-constexpr int KS_D_WARPS = 4;                  // warps 0..3: drain
-constexpr int KS_S_WARP = 4;                   // warp 4: stage
-constexpr int KS_A_WARPS = 27;                 // warps 5..31: expand
-constexpr int KS_X_THREADS = (KS_A_WARPS + 1) * 32;  // warps 4..31: the threads of the expansion-side barriers
-constexpr int KS_U = 2;                        // 16-byte chunks per lane per batch (ring: 32 bytes per lane)
-constexpr int KS_CH = 1024;                    // entries of a target row per pass
+constexpr int KS_D_WARPS = SPY_KS_D_WARPS;     // warps 0..D-1: drain (4 or 8: whole lane quarters)
+constexpr int KS_X_WARPS = 32 - KS_D_WARPS;    // warps D..31: expansion side; its first warp also runs the row queue
+constexpr int KS_A_WARPS = KS_X_WARPS - 1;     // warps D+1..31 expand
+constexpr int KS_X_THREADS = KS_X_WARPS * 32;
+constexpr int KS_DT = KS_D_WARPS * 32;
+constexpr int KS_U = SPY_KS_U;                 // 16-byte chunks per lane per batch (ring: 16 * KS_U bytes per lane)
+constexpr int KS_CH = 1024;                    // entries of a target row per pass (32 blocks of 32)
+constexpr int KS_CAP = 1024;                   // candidate buffer (keys); k <= KS_CAP / 2
 constexpr int KS_QCAP = 64;                    // quads per drain warp waiting for their per-slot test
 constexpr int KS_FLAG_PANEL_END = 1, KS_FLAG_ROW_END = 2, KS_FLAG_STOP = 4;
+static_assert(KS_D_WARPS == 4 || KS_D_WARPS == 8, "drain warps must cover whole lane quarters");
 
-struct KsPass {   // what the stage warp hands to the expansion warps (shared memory, double buffered)
-    int n;        // entries staged
-    unsigned total;  // chunks of the pass
+struct KsPass {   // one pass = up to KS_CH entries of a target row against one panel (shared memory, ring of 4)
+    long long aoff;  // first entry of the pass in aexp
+    int voff;        // ... and in a_data
+    int n;           // entries
     int pn, flags, t, i_out;
+};
+struct KsQueue {  // cursor of the row queue (shared memory; lane 0 of the queue warp)
+    long long tq0;
+    int have, i_out, t, a0, len, pn, c0;
 };
 struct KsMsg {    // what the expansion side hands to the drain with every snapshot (shared memory, double buffered)
     int t, i_out, pn, flags, landed;
 };
 
 __host__ __device__ constexpr size_t ks_ring_bytes() { return (size_t)KS_A_WARPS * 32 * KS_U * 16; }
-__host__ __device__ constexpr size_t ks_stage_bytes() { return (size_t)2 * ((KS_CH + 32) * 4 + KS_CH * 4 + KS_CH * 4); }
+__host__ __device__ constexpr size_t ks_stage_bytes() { return (size_t)2 * (3 * KS_CH * 4 + 32 * 4); }
 __host__ __device__ constexpr size_t ks_queue_bytes() { return (size_t)KS_D_WARPS * KS_QCAP * (16 + 4); }
-__host__ __device__ constexpr size_t ks_fixed_bytes(int cap) { return ks_ring_bytes() + ks_stage_bytes() + ks_queue_bytes() + (size_t)cap * 8; }
+__host__ __device__ constexpr size_t ks_fixed_bytes() { return ks_ring_bytes() + ks_stage_bytes() + ks_queue_bytes() + (size_t)KS_CAP * 8; }
 
 // ---- PTX helpers --------------------------------------------------------------------------------------------
 __device__ __forceinline__ void ks_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
@@ -88,7 +105,7 @@ __device__ __forceinline__ bool ks_mbar_try(unsigned bar, unsigned parity) {
     return ok != 0;
 }
 // bounded wait (about two seconds): a protocol bug must end in an error, not in a hung device
-__device__ __noinline__ void ks_timeout(int *err, int code) {
+static __device__ __noinline__ void ks_timeout(int *err, int code) {
     if (err) atomicExch(err, code);
     __threadfence_system();
     __trap();
@@ -113,21 +130,25 @@ __device__ __forceinline__ void ks_tmem_st4(unsigned taddr, float4 v) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(__float_as_uint(v.x)),
                  "r"(__float_as_uint(v.y)), "r"(__float_as_uint(v.z)), "r"(__float_as_uint(v.w)) : "memory");
 }
-__device__ __forceinline__ float4 ks_tmem_ld4(unsigned taddr) {
-    unsigned r0, r1, r2, r3;
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(taddr) : "memory");
+// four tiles (16 TMEM columns) of this warp's lane quarter: r[4 i + c] = slot c of the lane's quad in tile i
+__device__ __forceinline__ void ks_tmem_ld16(unsigned taddr, float (&r)[16]) {
+    unsigned u[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
+                   "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+                 : "r"(taddr) : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    return make_float4(__uint_as_float(r0), __uint_as_float(r1), __uint_as_float(r2), __uint_as_float(r3));
+#pragma unroll
+    for (int i = 0; i < 16; i++) r[i] = __uint_as_float(u[i]);
 }
 __device__ __forceinline__ void ks_tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void ks_tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// ---- drain side: sort / select with the 128 threads of the drain warps ---------------------------------------
-constexpr int KS_DT = KS_D_WARPS * 32;
+// ---- drain side: selection with the threads of the drain warps ---------------------------------------------------
 __device__ __forceinline__ void ks_dsync() { ks_bar_sync(4, KS_DT); }
 
 // Bitonic sort (descending) of cand[0, S), S a power of two; the drain warps only.
-__device__ void ks_bitonic_desc(u64 *cand, int S, int dtid) {
+static __device__ void ks_bitonic_desc(u64 *cand, int S, int dtid) {
     for (int size = 2; size <= S; size <<= 1) {
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
             for (int i = dtid; i < (S >> 1); i += KS_DT) {
@@ -141,9 +162,82 @@ __device__ void ks_bitonic_desc(u64 *cand, int S, int dtid) {
         }
     }
 }
+// One sampling round (see pivot_compact in knn_kernel.cuh): warp 0 sorts 64 strided samples in registers, the pivot sits
+// 3 sigma below the sample quantile of the k-th best; the keys above it are compacted IN PLACE (every thread holds its
+// keys in registers across the barrier that separates the reads from the writes).  Returns the new n, or -1 when the
+// pivot was unlucky (fewer than k keys above it): nothing has been moved then.
+static __device__ int ks_pivot_round(u64 *cand, int n, int k, int j, int *s_wsum, u64 *s_pivot, int dtid) {
+    constexpr int KPT = KS_CAP / KS_DT;  // keys per thread
+    const int lane = dtid & 31, w = dtid >> 5;
+    if (dtid < 32) {
+        u64 k0 = cand[(int)(((long long)dtid * n) >> 6)];
+        u64 k1 = cand[(int)(((long long)(dtid + 32) * n) >> 6)];
+#pragma unroll
+        for (int size = 2; size <= 64; size <<= 1) {
+#pragma unroll
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                if (stride == 32) {
+                    const u64 hi = k0 > k1 ? k0 : k1, lo = k0 > k1 ? k1 : k0;
+                    k0 = hi; k1 = lo;
+                } else {
+                    const u64 o0 = __shfl_xor_sync(0xffffffffu, k0, stride), o1 = __shfl_xor_sync(0xffffffffu, k1, stride);
+                    const bool lower = (dtid & stride) == 0;
+                    const bool desc0 = size == 64 || (size == 32 ? true : (dtid & size) == 0);
+                    const bool desc1 = size == 64 || (size == 32 ? false : (dtid & size) == 0);
+                    k0 = ((k0 > o0) == (lower == desc0)) ? k0 : o0;
+                    k1 = ((k1 > o1) == (lower == desc1)) ? k1 : o1;
+                }
+            }
+        }
+        const u64 pv = __shfl_sync(0xffffffffu, (j - 1) < 32 ? k0 : k1, (j - 1) & 31);
+        if (dtid == 0) *s_pivot = pv;
+    }
+    ks_dsync();
+    const u64 pivot = *s_pivot;
+    u64 kk[KPT];
+    int cnt = 0;
+#pragma unroll
+    for (int r = 0; r < KPT; r++) {
+        const int i = dtid + r * KS_DT;
+        kk[r] = i < n ? cand[i] : 0ull;
+        cnt += kk[r] > pivot ? 1 : 0;
+    }
+    int inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+    }
+    if (lane == 31) s_wsum[w] = inc;
+    ks_dsync();  // all keys are in registers; the warp totals are visible
+    int base = 0, total = 0;
+#pragma unroll
+    for (int i = 0; i < KS_D_WARPS; i++) {
+        const int v = s_wsum[i];
+        if (i < w) base += v;
+        total += v;
+    }
+    if (total >= k) {
+        int pos = base + inc - cnt;
+#pragma unroll
+        for (int r = 0; r < KPT; r++)
+            if (kk[r] > pivot) cand[pos++] = kk[r];
+    }
+    ks_dsync();
+    return total >= k ? total : -1;
+}
 // Exact selection among the evaluated keys cand[0, n) (0 = dead): leaves the best m = min(k, live) sorted best-first
 // in cand[0, m); returns m and, when m == k, sets tau to the k-th key.  (The reference's heap, s_plus.h:45-59.)
-__device__ int ks_select(u64 *cand, int n, int k, u64 &tau, int *s_live, int dtid) {
+// Sampling rounds shrink the set to a few hundred keys before the bitonic network; results never depend on the samples.
+static __device__ int ks_select(u64 *cand, int n, int k, u64 &tau, int *s_live, int *s_wsum, u64 *s_pivot, int dtid) {
+    for (int round = 0; round < 3; round++) {
+        const float qq = 65.f * (float)k / (float)max(n, 1);
+        const int j = (int)ceilf(qq + 3.f * sqrtf(qq) + 1.5f);
+        if (n <= 2 * k || n <= 192 || j > 40) break;
+        const int c = ks_pivot_round(cand, n, k, j, s_wsum, s_pivot, dtid);
+        if (c < 0) break;
+        n = c;
+    }
     int S = 32;
     while (S < n) S <<= 1;
     for (int i = n + dtid; i < S; i += KS_DT) cand[i] = 0ull;
@@ -159,6 +253,20 @@ __device__ int ks_select(u64 *cand, int n, int k, u64 &tau, int *s_live, int dti
     return m;
 }
 
+// -DSPY_KS_TIMING=1: cycle counters per role, summed over the CTAs into 24 u64 at the end of the scratch (development builds)
+#ifndef SPY_KS_TIMING
+#define SPY_KS_TIMING 0
+#endif
+#if SPY_KS_TIMING
+#define KS_T0(var) long long var = clock64()
+#define KS_ACC(id, var) do { const long long _n = clock64(); kt[id] += _n - var; var = _n; } while (0)
+#define KS_CNT(id, n) do { kt[id] += (n); } while (0)
+#else
+#define KS_T0(var) do { } while (0)
+#define KS_ACC(id, var) do { } while (0)
+#define KS_CNT(id, n) do { } while (0)
+#endif
+
 // The kernel.  KIND selects the drain's pre-filter like in knn_flat_kernel (KIND_RAW / _T / _C / _D / _GEN).
 template <int KIND>
 __global__ void __launch_bounds__(KS_NT, 1)
@@ -169,29 +277,34 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
     unsigned char *ptr = smem_raw + (size_t)q.W * sizeof(float);
     const unsigned ring32 = (unsigned)__cvta_generic_to_shared(ptr);
     ptr += ks_ring_bytes();
-    unsigned *stP[2], *stC[2];
-    float *stV[2];
-    for (int b = 0; b < 2; b++) {
-        stP[b] = reinterpret_cast<unsigned *>(ptr); ptr += (KS_CH + 32) * 4;
-        stC[b] = reinterpret_cast<unsigned *>(ptr); ptr += KS_CH * 4;
-        stV[b] = reinterpret_cast<float *>(ptr); ptr += KS_CH * 4;
-    }
+    // staged pass (double buffered): per entry the chunk count prefix INSIDE its block of 32 entries, the first chunk, the
+    // value; per block the chunk total
+    // (buffer b at stage0 + b * KS_STAGE_WORDS: prefixes [KS_CH], first chunks [KS_CH], values [KS_CH], block totals [32];
+    // plain pointer arithmetic -- an array of pointers indexed by the buffer number would live in local memory)
+    constexpr int KS_STAGE_WORDS = 3 * KS_CH + 32;
+    unsigned *const stage0 = reinterpret_cast<unsigned *>(ptr);
+    ptr += 2 * KS_STAGE_WORDS * 4;
     float4 *qx_all = reinterpret_cast<float4 *>(ptr); ptr += (size_t)KS_D_WARPS * KS_QCAP * 16;
     int *qc_all = reinterpret_cast<int *>(ptr); ptr += (size_t)KS_D_WARPS * KS_QCAP * 4;
     u64 *cand = reinterpret_cast<u64 *>(ptr);
 
     __shared__ __align__(8) unsigned long long s_full, s_empty;
-    __shared__ KsPass s_pass[2];
+    __shared__ __align__(8) u64 s_pivot;
+    __shared__ KsPass s_pass[4];
+    __shared__ KsQueue s_queue;
     __shared__ KsMsg s_msg[2];
     __shared__ unsigned s_tmem;
-    __shared__ int s_cnt, s_overflow, s_live;
+    __shared__ int s_cnt, s_overflow, s_live, s_wsum[KS_D_WARPS];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#if SPY_KS_TIMING
+    long long kt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
     const float sentinel = __uint_as_float(kSentinelBits);
     const float4 sentinel4 = make_float4(sentinel, sentinel, sentinel, sentinel);
     const unsigned acc32 = (unsigned)__cvta_generic_to_shared(acc);
     const unsigned full32 = (unsigned)__cvta_generic_to_shared(&s_full), empty32 = (unsigned)__cvta_generic_to_shared(&s_empty);
-    const int nT = q.W >> 9;  // tiles of 512 columns (W is a multiple of 512)
+    const int nT = q.W >> 9;  // tiles of 512 columns (W is a multiple of 2048: whole groups of four tiles)
 
     for (int i = tid * 4; i < q.W; i += KS_NT * 4) *reinterpret_cast<float4 *>(acc + i) = sentinel4;
     if (tid == 0) {
@@ -211,96 +324,107 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
 
     if (warp >= KS_D_WARPS) {
         // =====================================================================================================
-        // expansion side: warp 4 stages, warps 5..31 expand, all 28 take the snapshots
+        // expansion side
         // =====================================================================================================
-        const bool is_stage = warp == KS_S_WARP;
-        const int wa = warp - (KS_S_WARP + 1);  // 0..26 for the expansion warps
-        // ---- stage warp state (uniform registers) ----
-        bool s_have = false;
-        int s_i_out = 0, s_t = 0, s_a0 = 0, s_len = 0, s_pn = 0, s_c0 = 0;
-        long long s_tq0 = 0;
-        auto stage_next = [&](int buf) {  // prepare the next pass into buffer `buf`
-            KsPass *d = &s_pass[buf];
-            if (!s_have) {
-                int slot = 0;
-                if (lane == 0) slot = atomicAdd(q.work_counter, 1);
-                slot = __shfl_sync(0xffffffffu, slot, 0);
+        const int wx = warp - KS_D_WARPS;     // 0..KS_X_WARPS-1; warp 0 of the side runs the row queue instead of expanding
+        const bool is_queue = wx == 0;
+        const int wa = wx - 1;                // 0..KS_A_WARPS-1 for the expansion warps
+        // ---- row queue: lane 0 of the side's first warp; its cursor (the pass AFTER the last one described) lives in shared
+        //      memory so that it does not occupy registers of the expansion warps ----
+        auto describe_next = [&](KsPass *d) {  // lane 0 of the queue warp only
+            KsQueue &c = s_queue;
+            if (!c.have) {
+                const int slot = atomicAdd(q.work_counter, 1);
                 if (slot >= q.n_targets) {
-                    if (lane == 0) { d->n = 0; d->total = 0u; d->pn = 0; d->flags = KS_FLAG_STOP; d->t = 0; d->i_out = 0; }
+                    d->aoff = 0; d->voff = 0; d->n = 0; d->pn = 0; d->flags = KS_FLAG_STOP; d->t = 0; d->i_out = 0;
                     return;
                 }
-                s_i_out = q.row_order ? __ldg(q.row_order + slot) : slot;
-                s_t = __ldg(q.targets + s_i_out);
-                s_a0 = __ldg(q.a_indptr + s_t);
-                s_len = __ldg(q.a_indptr + s_t + 1) - s_a0;
-                s_tq0 = __ldg(p.toff + s_i_out);
-                s_pn = 0; s_c0 = 0; s_have = true;
-                if (s_len <= 0) {  // empty row: one message so that the drain writes its (empty) output
-                    if (lane == 0) { d->n = 0; d->total = 0u; d->pn = q.n_panels - 1; d->flags = KS_FLAG_PANEL_END | KS_FLAG_ROW_END; d->t = s_t; d->i_out = s_i_out; }
-                    s_have = false;
+                c.i_out = q.row_order ? __ldg(q.row_order + slot) : slot;
+                c.t = __ldg(q.targets + c.i_out);
+                c.a0 = __ldg(q.a_indptr + c.t);
+                c.len = __ldg(q.a_indptr + c.t + 1) - c.a0;
+                c.tq0 = __ldg(p.toff + c.i_out);
+                c.pn = 0; c.c0 = 0; c.have = 1;
+                if (c.len <= 0) {  // empty row: one message so that the drain writes its (empty) output
+                    d->aoff = 0; d->voff = 0; d->n = 0; d->pn = q.n_panels - 1; d->flags = KS_FLAG_PANEL_END | KS_FLAG_ROW_END;
+                    d->t = c.t; d->i_out = c.i_out;
+                    c.have = 0;
                     return;
                 }
             }
-            const int n = min(KS_CH, s_len - s_c0);
-            const uint2 *src = p.aexp + ((long long)s_pn * p.E + s_tq0 + s_c0);
-            const float *vsrc = q.a_data + s_a0 + s_c0;
-            unsigned *sP = stP[buf], *sC = stC[buf];
-            float *sV = stV[buf];
-            unsigned carry = 0u;
-            for (int r0 = 0; r0 < n; r0 += 256) {
-                uint2 se[8];
-                float vv[8];
-#pragma unroll
-                for (int r = 0; r < 8; r++) {
-                    const int i = r0 + r * 32 + lane;
-                    se[r] = make_uint2(0u, 0u); vv[r] = 0.f;
-                    if (i < n) { se[r] = __ldg(src + i); vv[r] = __ldg(vsrc + i); }
-                }
-#pragma unroll
-                for (int r = 0; r < 8; r++) {
-                    const int i = r0 + r * 32 + lane;
-                    if (r0 + r * 32 < n) {  // uniform
-                        const unsigned c = se[r].y - se[r].x;
-                        unsigned inc = c;
-#pragma unroll
-                        for (int o = 1; o < 32; o <<= 1) {
-                            const unsigned v = __shfl_up_sync(0xffffffffu, inc, o);
-                            if (lane >= o) inc += v;
-                        }
-                        if (i < n) { sP[i] = carry + inc - c; sC[i] = se[r].x; sV[i] = vv[r]; }
-                        carry += __shfl_sync(0xffffffffu, inc, 31);
-                    }
-                }
-            }
+            const int n = min(KS_CH, c.len - c.c0);
             int flags = 0;
-            if (s_c0 + n == s_len) {
+            if (c.c0 + n == c.len) {
                 flags |= KS_FLAG_PANEL_END;
-                if (s_pn == q.n_panels - 1) flags |= KS_FLAG_ROW_END;
+                if (c.pn == q.n_panels - 1) flags |= KS_FLAG_ROW_END;
             }
-            if (lane == 0) { sP[n] = carry; d->n = n; d->total = carry; d->pn = s_pn; d->flags = flags; d->t = s_t; d->i_out = s_i_out; }
-            s_c0 += n;
-            if (s_c0 == s_len) { s_c0 = 0; s_pn++; if (s_pn == q.n_panels) s_have = false; }
+            d->aoff = (long long)c.pn * p.E + c.tq0 + c.c0; d->voff = c.a0 + c.c0; d->n = n; d->pn = c.pn; d->flags = flags;
+            d->t = c.t; d->i_out = c.i_out;
+            c.c0 += n;
+            if (c.c0 == c.len) { c.c0 = 0; c.pn++; if (c.pn == q.n_panels) c.have = 0; }
+        };
+        // ---- staging of a pass: expansion warp wa owns block wa of 32 entries (loads at the start of the current pass, scan
+        //      + store at its end); the queue warp, idle otherwise, takes blocks KS_A_WARPS..31 ----
+        uint2 g_se = make_uint2(0u, 0u);
+        float g_v = 0.f;
+        auto stage_block = [&](int buf, int b, uint2 se, float v) {  // scan of the block's chunk counts, store
+            const unsigned c = se.y - se.x;
+            unsigned inc = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned u = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += u;
+            }
+            unsigned *st = stage0 + buf * KS_STAGE_WORDS;
+            const int i = b * 32 + lane;
+            st[i] = inc - c; st[KS_CH + i] = se.x; st[2 * KS_CH + i] = __float_as_uint(v);
+            if (lane == 31) st[3 * KS_CH + b] = inc;
+        };
+        auto stage_fetch = [&](const KsPass &d, int b, uint2 &se, float &v) {
+            const int i = b * 32 + lane;
+            se = make_uint2(0u, 0u); v = 0.f;
+            if (i < d.n) {
+                se = __ldg(p.aexp + d.aoff + i); v = __ldg(q.a_data + d.voff + i);
+#if SPY_KS_PREFETCH
+                // the segment's chunks -> L2, a whole pass before the ring asks for them (exact bytes: no line over-fetch)
+                if (se.y > se.x) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.chunks + se.x), "r"((se.y - se.x) * 16u) : "memory");
+#endif
+            }
+        };
+        auto stage_queue_blocks = [&](const KsPass &d, int buf) {  // the queue warp's share, start to end
+            for (int b0 = KS_A_WARPS; b0 < 32; b0 += 3) {
+                uint2 se[3];
+                float v[3];
+#pragma unroll
+                for (int r = 0; r < 3; r++) { se[r] = make_uint2(0u, 0u); v[r] = 0.f; if (b0 + r < 32) stage_fetch(d, b0 + r, se[r], v[r]); }
+#pragma unroll
+                for (int r = 0; r < 3; r++) if (b0 + r < 32) stage_block(buf, b0 + r, se[r], v[r]);
+            }
         };
 
         // ---- expansion warp state ----
         const unsigned slot32 = ring32 + (unsigned)((max(wa, 0) * 32 * KS_U + lane) * 16);  // chunk r of a batch: + r * 512
         unsigned f = 0u, fb = 0u, F1 = 0u;  // next chunk to issue, end of the sub-batch, end of the warp's range (uniform)
         int j0 = 0, n_cur = 0;
+        unsigned boff = 0u, total = 0u;      // lane b: chunks before block b of the pass; chunks of the pass
         unsigned Pe = 0u, Pi = 0u, C0 = 0u;  // lane l: segment j0 + l of the pass: first chunk number, end, first chunk in `chunks`
         float V = 0.f;
-        const unsigned *cP = nullptr, *cC = nullptr;
-        const float *cV = nullptr;
+        const unsigned *cP = nullptr;  // staged pass: prefixes; first chunks at + KS_CH, values at + 2 KS_CH
         float vp[KS_U];
         unsigned lp = 0u;
 #pragma unroll
         for (int r = 0; r < KS_U; r++) vp[r] = 0.f;
+        auto prefix_at = [&](int idx) -> unsigned {  // chunks of the pass before segment idx (all lanes call it together)
+            const unsigned o = __shfl_sync(0xffffffffu, boff, min(idx, KS_CH - 1) >> 5);
+            return idx >= n_cur ? total : cP[idx] + o;
+        };
         auto issue = [&]() {  // one batch of KS_U chunks per lane into the ring
             if (f >= fb) {    // next 32 segments (uniform)
                 const int idx = j0 + lane;
-                Pe = cP[min(idx, n_cur)];
-                Pi = cP[min(idx + 1, n_cur)];
-                C0 = cC[min(idx, n_cur - 1)];
-                V = cV[min(idx, n_cur - 1)];
+                Pe = prefix_at(idx);
+                Pi = prefix_at(idx + 1);
+                C0 = cP[KS_CH + min(idx, n_cur - 1)];
+                V = __uint_as_float(cP[2 * KS_CH + min(idx, n_cur - 1)]);
                 fb = min(F1, __shfl_sync(0xffffffffu, Pi, 31));
                 j0 += 32;
             }
@@ -326,33 +450,35 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
             f = min(f + 32u * KS_U, fb);
         };
 
-        // ---- snapshot bookkeeping (uniform over the 28 warps) ----
+        // ---- snapshot bookkeeping (uniform over the warps of the side) ----
         unsigned seq = 0u;  // snapshots / messages posted so far
-        bool pending = false, panel_landed = false;
-        int m_t = 0, m_i_out = 0, m_pn = 0, m_flags = 0, m_landed = 0;
+        bool pending = false, panel_landed = false, m_landed = false;
         auto post = [&](int t, int i_out, int pn, int flags, int landed) {  // one thread: message + "snapshot full"
             KsMsg *m = &s_msg[seq & 1u];
             m->t = t; m->i_out = i_out; m->pn = pn; m->flags = flags; m->landed = landed;
             ks_mbar_arrive(full32);
         };
-        auto snapshot = [&]() {
+        auto snapshot = [&](const KsPass &dp) {  // dp: the pass that completed the panel
+            KS_T0(ts);
+            const int m_t = dp.t, m_pn = dp.pn;
             // the drain must have released the previous snapshot (and read its message)
             if (lane == 0) ks_mbar_wait(empty32, (seq & 1u) ^ 1u, p.err, 2);
             __syncwarp();
+            KS_ACC(4, ts);
             ks_tc_fence_after();
             if (m_landed) {
                 const int base = m_pn * q.W;
                 if (q.filter_mode == SPY_SEL_MATRIX) {  // erase the row's filtered columns first (s_plus.h:159-172)
                     const int width = min(q.W, q.n_cols - base);
                     const int fs = __ldg(q.f_indptr + m_t), fe = __ldg(q.f_indptr + m_t + 1);
-                    for (int x = fs + (tid - KS_D_WARPS * 32); x < fe; x += KS_X_THREADS) {
+                    for (int x = fs + (tid - KS_DT); x < fe; x += KS_X_THREADS) {
                         const int c = __ldg(q.f_indices + x) - base;
                         if (c >= 0 && c < width) acc[c] = sentinel;
                     }
                     ks_bar_sync(3, KS_X_THREADS);
                 }
-                const int sub = (warp - KS_D_WARPS) >> 2;  // 0..6: the warps of one lane quarter
-                for (int T = sub; T < nT; T += 7) {
+                const int sub = wx >> 2;  // the warps of one lane quarter take every (KS_X_WARPS / 4)-th tile
+                for (int T = sub; T < nT; T += KS_X_WARPS / 4) {
                     const unsigned a = acc32 + (unsigned)(512 * T + 128 * (warp & 3) + 4 * lane) * 4u;
                     const float4 x = lds128(a);
                     sts128(a, sentinel4);
@@ -362,91 +488,140 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
             }
             ks_tc_fence_before();
             ks_bar_sync(2, KS_X_THREADS);  // every slot of the panel is in TMEM and reset
-            if (tid == KS_D_WARPS * 32) post(m_t, m_i_out, m_pn, m_flags, m_landed);
+            if (tid == KS_DT) post(dp.t, dp.i_out, dp.pn, dp.flags, m_landed ? 1 : 0);
             seq++;
+            KS_ACC(3, ts);
         };
 
-        if (is_stage) stage_next(0);
+        // ---- prologue: describe passes 0 and 1, stage pass 0 ----
+        if (tid == KS_DT) {
+            s_queue.have = 0;
+            describe_next(&s_pass[0]);
+            if (s_pass[0].flags & KS_FLAG_STOP) { s_pass[1].flags = KS_FLAG_STOP; s_pass[1].n = 0; }
+            else describe_next(&s_pass[1]);
+        }
         ks_bar_sync(1, KS_X_THREADS);
+        {
+            const KsPass d0 = s_pass[0];
+            if (is_queue) stage_queue_blocks(d0, 0);
+            else { stage_fetch(d0, wa, g_se, g_v); stage_block(0, wa, g_se, g_v); }
+        }
+        ks_bar_sync(1, KS_X_THREADS);
+        KS_T0(tp);
         for (int pass = 0;; pass++) {
             const int buf = pass & 1;
-            const KsPass d = s_pass[buf];
+            const KsPass d = s_pass[pass & 3];
+            const KsPass dn = s_pass[(pass + 1) & 3];
             const bool stop = (d.flags & KS_FLAG_STOP) != 0;
+            const bool stage_next = !stop && !(dn.flags & KS_FLAG_STOP);
             bool have = false;
-            unsigned accb32 = 0u, base = 0u;
-            if (!is_stage && !stop) {  // this warp's chunk range of the pass and its first batch
-                n_cur = d.n; cP = stP[buf]; cC = stC[buf]; cV = stV[buf];
-                base = (unsigned)d.pn * (unsigned)q.W;
-                accb32 = acc32 - base * 4u;
-                const unsigned F0 = (unsigned)(((unsigned long long)d.total * (unsigned)wa) / KS_A_WARPS);
-                F1 = (unsigned)(((unsigned long long)d.total * (unsigned)(wa + 1)) / KS_A_WARPS);
-                f = F0; fb = F0;
-                if (F0 < F1) {
-                    // j0 = the last segment that starts at or before chunk F0 (two rounds of 32 probes)
-                    int idx = lane * 32;
-                    unsigned v = idx <= n_cur ? cP[idx] : 0xffffffffu;
-                    const int blk = __popc(__ballot_sync(0xffffffffu, v <= F0)) - 1;
-                    idx = blk * 32 + lane;
-                    v = idx <= n_cur ? cP[idx] : 0xffffffffu;
-                    j0 = blk * 32 + __popc(__ballot_sync(0xffffffffu, v <= F0)) - 1;
-                    issue();
-                    have = true;
+            unsigned base = 0u;
+            if (!stop) {
+                // chunks before every block of the pass (lane b: block b) and the pass total
+                const unsigned *st = stage0 + buf * KS_STAGE_WORDS;
+                const unsigned bt = st[3 * KS_CH + lane];
+                unsigned inc = bt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned v = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += v;
                 }
-            }
-            if (pending) snapshot();
-            if (stop) break;
-            bool any = false;
-            if (is_stage) stage_next(buf ^ 1);
-            else {
-                any = have;
-                while (have) {
-                    ks_cp_wait_all();
-                    uint4 pr[KS_U];
-                    float vc[KS_U];
-#pragma unroll
-                    for (int r = 0; r < KS_U; r++) { pr[r] = ks_lds128u(slot32 + (unsigned)r * 512u); vc[r] = vp[r]; }
-                    const unsigned lc = lp;
-                    const bool more = f < F1;
-                    if (more) issue();
-#pragma unroll
-                    for (int r = 0; r < KS_U; r++) {
-                        if (lc & (1u << r)) {
-                            const unsigned d0 = pr[r].x - base, d1 = pr[r].z - base;
-                            if (d0 < (unsigned)q.W) smem_add_f32(acc32 + d0 * 4u, __fmul_rn(__uint_as_float(pr[r].y), vc[r]));
-                            if (d1 < (unsigned)q.W) smem_add_f32(acc32 + d1 * 4u, __fmul_rn(__uint_as_float(pr[r].w), vc[r]));
-                        }
+                boff = inc - bt;
+                total = __shfl_sync(0xffffffffu, inc, 31);
+                if (!is_queue) {  // this warp's chunk range of the pass and its first batch
+                    n_cur = d.n; cP = st;
+                    base = (unsigned)d.pn * (unsigned)q.W;
+                    const unsigned F0 = (unsigned)(((unsigned long long)total * (unsigned)wa) / KS_A_WARPS);
+                    F1 = (unsigned)(((unsigned long long)total * (unsigned)(wa + 1)) / KS_A_WARPS);
+                    f = F0; fb = F0;
+                    if (F0 < F1) {
+                        // j0 = the last segment that starts at or before chunk F0: first its block, then inside the block
+                        const int blk = __popc(__ballot_sync(0xffffffffu, lane * 32 <= n_cur && boff <= F0)) - 1;
+                        const unsigned v = prefix_at(blk * 32 + lane);
+                        j0 = blk * 32 + __popc(__ballot_sync(0xffffffffu, blk * 32 + lane <= n_cur && v <= F0)) - 1;
+                        issue();
+                        have = true;
                     }
-                    have = more;
                 }
             }
-            (void)accb32;
+            if (stage_next && !is_queue) stage_fetch(dn, wa, g_se, g_v);  // pass + 1: the loads land during this pass
+            if (is_queue && !stop) {
+                if (lane == 0) {  // pass + 2
+                    if (stage_next) describe_next(&s_pass[(pass + 2) & 3]);
+                    else { s_pass[(pass + 2) & 3].flags = KS_FLAG_STOP; s_pass[(pass + 2) & 3].n = 0; }  // (STOP stays STOP)
+                }
+                __syncwarp();
+            }
+            KS_ACC(5, tp);
+            if (pending) snapshot(s_pass[(pass + 3) & 3]);  // (pass - 1: its slot is rewritten two passes from now)
+            if (stop) break;
+            KS_ACC(0, tp);  // (the snapshot, also counted in [3] / [4])
+            const bool any = have;
+            while (have) {
+                ks_cp_wait_all();
+                uint4 pr[KS_U];
+                float vc[KS_U];
+#pragma unroll
+                for (int r = 0; r < KS_U; r++) { pr[r] = ks_lds128u(slot32 + (unsigned)r * 512u); vc[r] = vp[r]; }
+                const unsigned lc = lp;
+                const bool more = f < F1;
+                if (more) issue();
+#pragma unroll
+                for (int r = 0; r < KS_U; r++) {
+                    if (lc & (1u << r)) {
+                        const unsigned d0 = pr[r].x - base, d1 = pr[r].z - base;
+#ifdef SPY_KS_NOADDS  // timing experiment: gathers only (results are wrong)
+                        if (d0 + d1 == 0x12345u) smem_add_f32(acc32, vc[r]);
+#else
+                        if (d0 < (unsigned)q.W) smem_add_f32(acc32 + d0 * 4u, __fmul_rn(__uint_as_float(pr[r].y), vc[r]));
+                        if (d1 < (unsigned)q.W) smem_add_f32(acc32 + d1 * 4u, __fmul_rn(__uint_as_float(pr[r].w), vc[r]));
+#endif
+                    }
+                }
+                have = more;
+            }
+            KS_ACC(1, tp);
+            if (stage_next) {
+                if (is_queue) stage_queue_blocks(dn, buf ^ 1);
+                else stage_block(buf ^ 1, wa, g_se, g_v);
+            }
+            KS_ACC(6, tp);
             const bool landed = ks_bar_or(1, KS_X_THREADS, any);  // all adds of the pass have landed; the next pass is staged
+            KS_ACC(2, tp);
             panel_landed |= landed;
             pending = false;
             if (d.flags & KS_FLAG_PANEL_END) {
-                if (panel_landed || (d.flags & KS_FLAG_ROW_END)) {
-                    pending = true;
-                    m_t = d.t; m_i_out = d.i_out; m_pn = d.pn; m_flags = d.flags; m_landed = panel_landed ? 1 : 0;
-                }
+                if (panel_landed || (d.flags & KS_FLAG_ROW_END)) { pending = true; m_landed = panel_landed; }
                 panel_landed = false;
             }
         }
         // no more rows: tell the drain
-        if (tid == KS_D_WARPS * 32) {
+        if (tid == KS_DT) {
             ks_mbar_wait(empty32, (seq & 1u) ^ 1u, p.err, 3);
             post(0, 0, 0, KS_FLAG_STOP, 0);
         }
+#if SPY_KS_TIMING
+        // [0] snapshot  [1] pass body  [2] end-of-pass barrier  [3] snapshot (again)  [4] wait for the drain  [5] pass setup + first issue
+        // [6] staging of the next pass; the first expansion warp reports into 0..6, the queue warp into 8..14
+        if (lane == 0 && (wx == 1 || wx == 0))
+            for (int i = 0; i < 7; i++) atomicAdd(q.phase + (wx == 0 ? 8 : 0) + i, (u64)kt[i]);
+#endif
     } else {
         // =====================================================================================================
-        // drain side: warps 0..3, warp w reads lane quarter w of the snapshot
+        // drain side: warp w reads lane quarter w % 4 of the snapshot; with 8 warps the two warps of a quarter alternate
+        // over the groups of four tiles
         // =====================================================================================================
-        const int dtid = tid;  // 0..127
+        const int dtid = tid;
+        constexpr int DPQ = KS_D_WARPS / 4;  // warps per lane quarter
+        const int dsub = warp >> 2, quarter = warp & 3;
         float4 *qx = qx_all + warp * KS_QCAP;
         int *qc = qc_all + warp * KS_QCAP;
         const bool filter = !q.exact_only;
         const bool useT = filter && (KIND == KIND_T || (KIND == KIND_GEN && q.l1 != 0.f));
         const bool useC = filter && (KIND == KIND_C || (KIND == KIND_GEN && q.l2 != 0.f));
         const bool useD = filter && (KIND == KIND_D || (KIND == KIND_GEN && q.l3 != 0.f));
+        const int nG = nT >> 2;                                // groups of four tiles
+        const int nGloc = (nG - dsub + DPQ - 1) / DPQ;         // groups of this warp's sweep
         bool row_open = false;
         SimRow sr = {0.f, 0.f, 0.f};
         FastRow fr = {0.f, 0.f, 0.f, 0.f, 0.f};
@@ -471,18 +646,21 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
         };
         auto select_now = [&]() {  // evaluate what is buffered, keep the best k, raise tau
             ks_dsync();
-            const int cnt = min(*reinterpret_cast<volatile int *>(&s_cnt), q.cap);
+            const int cnt = min(*reinterpret_cast<volatile int *>(&s_cnt), KS_CAP);
             evaluate(cnt);
-            const int m = ks_select(cand, cnt, q.k, tau, &s_live, dtid);
+            ks_dsync();
+            const int m = ks_select(cand, cnt, q.k, tau, &s_live, s_wsum, &s_pivot, dtid);
             lo = reject_bound(q, tau);
             n_eval = m;
             if (dtid == 0) { s_cnt = m; s_overflow = 0; }
             ks_dsync();
         };
 
+        KS_T0(td);
         for (unsigned seq = 0u;; seq++) {
             if (lane == 0) ks_mbar_wait(full32, seq & 1u, p.err, 1);
             __syncwarp();
+            KS_ACC(0, td);
             const KsMsg m = s_msg[seq & 1u];
             if (m.flags & KS_FLAG_STOP) break;
             ks_tc_fence_after();
@@ -500,9 +678,13 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
                 lo = reject_bound(q, tau);
                 n_eval = 0;  // (s_cnt was reset when the previous row was written)
             }
+#ifdef SPY_KS_NODRAIN  // timing experiment: the drain releases the snapshot unread (results are wrong)
+            if (false) {
+#else
             if (m.landed) {
+#endif
                 const int base = m.pn * q.W;
-                int Tcur = 0, qn = 0;  // next tile of this warp's sweep; quads waiting in the warp's queue
+                int gi = 0, i_res = 0, qn = 0;  // next group of four tiles of this warp's sweep, first tile of it still to do; queued quads
                 for (;;) {  // sweep; leaves the loop when the warp's share is done; re-entered after an overflow
                     bool overflow = false;
                     // coarse bound of a tile (per 128-column block of this warp's lane quarter): a slot can only enter the
@@ -511,103 +693,124 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
                     const float g = 1.f - lo * fr.cX;
                     const bool coarse = filter && lo > 0.f && g > 0.f && fr.cT >= 0.f && fr.cC >= 0.f && fr.cD >= 0.f &&
                                         (!useT || p.ymin_t != nullptr) && (!useC || p.ymin_c != nullptr) && (!useD || p.ymin_d != nullptr);
-                    float cb[4] = {0.f, 0.f, 0.f, 0.f};
+                    float cb0 = 0.f, cb1 = 0.f, cb2 = 0.f, cb3 = 0.f;
                     if (coarse) {
-#pragma unroll
-                        for (int ri = 0; ri < 4; ri++) {
-                            const int T = lane + 32 * ri;
-                            const int blk = (base >> 7) + 4 * T + warp;
-                            if (T < nT && blk < ((q.n_cols + 127) >> 7)) {
-                                float dmin = fr.A0;
-                                if (useT) dmin = fmaf(fr.cT, __ldg(p.ymin_t + blk), dmin);
-                                if (useC) dmin = fmaf(fr.cC, __ldg(p.ymin_c + blk), dmin);
-                                if (useD) dmin = fmaf(fr.cD, __ldg(p.ymin_d + blk), dmin);
-                                cb[ri] = (KIND == KIND_RAW) ? lo : (dmin > 0.f ? lo * dmin / g : 0.f);
-                            }
-                        }
+                        auto tile_bound = [&](int T) -> float {
+                            const int blk = (base >> 7) + 4 * T + quarter;
+                            if (T >= nT || blk >= ((q.n_cols + 127) >> 7)) return 0.f;
+                            float dmin = fr.A0;
+                            if (useT) dmin = fmaf(fr.cT, __ldg(p.ymin_t + blk), dmin);
+                            if (useC) dmin = fmaf(fr.cC, __ldg(p.ymin_c + blk), dmin);
+                            if (useD) dmin = fmaf(fr.cD, __ldg(p.ymin_d + blk), dmin);
+                            return (KIND == KIND_RAW) ? lo : (dmin > 0.f ? lo * dmin / g : 0.f);
+                        };
+                        cb0 = tile_bound(lane); cb1 = tile_bound(lane + 32); cb2 = tile_bound(lane + 64); cb3 = tile_bound(lane + 96);
                     }
-                    while (Tcur < nT || qn > 0) {
-                        if (qn >= 32 || Tcur >= nT) {
-                            // ---- per-slot test of up to 32 queued quads, all lanes busy: one L2 round trip for the batch ----
-                            const int nb = min(qn, 32);
-                            const int e = qn - nb + lane;  // take from the end of the queue
-                            unsigned sm = 0u;
-                            float4 x = sentinel4;
-                            int col0 = 0;
-                            if (lane < nb) {
-                                x = qx[e]; col0 = qc[e];
-                                float4 yt = sentinel4, yc = sentinel4, yd = sentinel4;
-                                if (col0 + 3 < q.n_cols) {
-                                    if (useT) yt = __ldg(reinterpret_cast<const float4 *>(q.Yt + col0));
-                                    if (useC) yc = __ldg(reinterpret_cast<const float4 *>(q.Yc + col0));
-                                    if (useD) yd = __ldg(reinterpret_cast<const float4 *>(q.Yd + col0));
-                                } else {
-                                    if (useT) yt = load_y4(q.Yt, col0, q.n_cols);
-                                    if (useC) yc = load_y4(q.Yc, col0, q.n_cols);
-                                    if (useD) yd = load_y4(q.Yd, col0, q.n_cols);
-                                }
-                                const float lc = lo * (KIND == KIND_D ? fr.cD : fr.cC), la = lo * fr.A0;
-                                sm = survivor_mask<KIND>(q, fr, filter, lo, lc, la, x, yt, yc, yd);
+                    const float lc = lo * (KIND == KIND_D ? fr.cD : fr.cC), la = lo * fr.A0;
+                    // per-slot test of up to 32 queued quads, all lanes busy: one L2 round trip for the batch; false = buffer full
+                    auto batch = [&]() -> bool {
+                        __syncwarp();
+                        const int nb = min(qn, 32);
+                        const int e = qn - nb + lane;  // take from the end of the queue
+                        unsigned sm = 0u;
+                        float4 x = sentinel4;
+                        int col0 = 0;
+                        if (lane < nb) {
+                            x = qx[e]; col0 = qc[e];
+                            float4 yt = sentinel4, yc = sentinel4, yd = sentinel4;
+                            if (col0 + 3 < q.n_cols) {
+                                if (useT) yt = __ldg(reinterpret_cast<const float4 *>(q.Yt + col0));
+                                if (useC) yc = __ldg(reinterpret_cast<const float4 *>(q.Yc + col0));
+                                if (useD) yd = __ldg(reinterpret_cast<const float4 *>(q.Yd + col0));
+                            } else {
+                                if (useT) yt = load_y4(q.Yt, col0, q.n_cols);
+                                if (useC) yc = load_y4(q.Yc, col0, q.n_cols);
+                                if (useD) yd = load_y4(q.Yd, col0, q.n_cols);
                             }
-                            const int c = __popc(sm);
-                            int inc = c;
-#pragma unroll
-                            for (int o = 1; o < 32; o <<= 1) {
-                                const int v = __shfl_up_sync(0xffffffffu, inc, o);
-                                if (lane >= o) inc += v;
-                            }
-                            const int total = __shfl_sync(0xffffffffu, inc, 31);
-                            if (total > 0) {
-                                int pos = 0;
-                                if (lane == 31) pos = atomicAdd(&s_cnt, total);
-                                pos = __shfl_sync(0xffffffffu, pos, 31);
-                                if (pos + total > q.cap) {  // does not fit: dead fillers, select, come back
-                                    for (int i = pos + lane; i < min(pos + total, q.cap); i += 32) cand[i] = 0xffffffffull;
-                                    overflow = true;
-                                    break;
-                                }
-                                int w = pos + inc - c;
-                                const float xs[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-                                for (int r = 0; r < 4; r++)
-                                    if (sm & (1u << r)) cand[w++] = make_raw(xs[r], col0 + r);
-                            }
-                            qn -= nb;
-                            continue;
+                            sm = survivor_mask<KIND>(q, fr, filter, lo, lc, la, x, yt, yc, yd);
                         }
-                        // ---- coarse test of the next tile: quads that cannot be rejected as a whole join the queue ----
-                        const float4 x = ks_tmem_ld4(tmem_q + (unsigned)(4 * Tcur));
+                        const int c = __popc(sm);
+                        int inc = c;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const int v = __shfl_up_sync(0xffffffffu, inc, o);
+                            if (lane >= o) inc += v;
+                        }
+                        const int tot = __shfl_sync(0xffffffffu, inc, 31);
+                        if (tot > 0) {
+                            int pos = 0;
+                            if (lane == 31) pos = atomicAdd(&s_cnt, tot);
+                            pos = __shfl_sync(0xffffffffu, pos, 31);
+                            if (pos + tot > KS_CAP) {  // does not fit: dead fillers, select, come back (the quads stay queued)
+                                for (int i = pos + lane; i < min(pos + tot, KS_CAP); i += 32) cand[i] = 0xffffffffull;
+                                return false;
+                            }
+                            int w = pos + inc - c;
+                            if (sm & 1u) cand[w++] = make_raw(x.x, col0);
+                            if (sm & 2u) cand[w++] = make_raw(x.y, col0 + 1);
+                            if (sm & 4u) cand[w++] = make_raw(x.z, col0 + 2);
+                            if (sm & 8u) cand[w++] = make_raw(x.w, col0 + 3);
+                        }
+                        qn -= nb;
+                        KS_CNT(6, 1);
+                        return true;
+                    };
+                    // coarse test of one tile: quads that cannot be rejected as a whole join the queue
+                    auto tile = [&](int T, const float4 x) {
                         bool pass;
-                        const bool touched = (__float_as_uint(x.x) != kSentinelBits) | (__float_as_uint(x.y) != kSentinelBits) |
-                                             (__float_as_uint(x.z) != kSentinelBits) | (__float_as_uint(x.w) != kSentinelBits);
                         if (coarse) {
-                            const int ri = Tcur >> 5;
-                            const float mine = ri == 0 ? cb[0] : ri == 1 ? cb[1] : ri == 2 ? cb[2] : cb[3];
-                            const float bound = __shfl_sync(0xffffffffu, mine, Tcur & 31);
-                            if (KIND == KIND_RAW || KIND == KIND_C || KIND == KIND_D)  // den >= 0: a negative dot product never passes lo > 0
-                                pass = !((x.x < bound) & (x.y < bound) & (x.z < bound) & (x.w < bound));
-                            else  // a negative dot product over a negative denominator is left to the per-slot test
-                                pass = !((x.x < bound) & (x.y < bound) & (x.z < bound) & (x.w < bound)) | (x.x < 0.f) | (x.y < 0.f) |
-                                       (x.z < 0.f) | (x.w < 0.f);
-                            pass &= touched;
-                        } else pass = touched;
+                            const int ri = T >> 5;
+                            const float mine = ri == 0 ? cb0 : ri == 1 ? cb1 : ri == 2 ? cb2 : cb3;
+                            const float bound = __shfl_sync(0xffffffffu, mine, T & 31);
+                            // (an untouched slot holds -0.0f: it fails x >= bound for every bound > 0)
+                            pass = (x.x >= bound) | (x.y >= bound) | (x.z >= bound) | (x.w >= bound);
+                            if (bound <= 0.f || !(KIND == KIND_RAW || KIND == KIND_C || KIND == KIND_D)) {
+                                // no usable bound for the block: every touched slot goes on; and where the denominator may be
+                                // negative a negative dot product is left to the per-slot test
+                                const bool touched = (__float_as_uint(x.x) != kSentinelBits) | (__float_as_uint(x.y) != kSentinelBits) |
+                                                     (__float_as_uint(x.z) != kSentinelBits) | (__float_as_uint(x.w) != kSentinelBits);
+                                if (bound <= 0.f) pass = touched;
+                                else pass = (pass | (x.x < 0.f) | (x.y < 0.f) | (x.z < 0.f) | (x.w < 0.f)) & touched;
+                            }
+                        } else {
+                            pass = (__float_as_uint(x.x) != kSentinelBits) | (__float_as_uint(x.y) != kSentinelBits) |
+                                   (__float_as_uint(x.z) != kSentinelBits) | (__float_as_uint(x.w) != kSentinelBits);
+                        }
                         const unsigned bal = __ballot_sync(0xffffffffu, pass);
                         if (pass) {
                             const int e = qn + __popc(bal & ((1u << lane) - 1u));
                             qx[e] = x;
-                            qc[e] = base + 512 * Tcur + 128 * warp + 4 * lane;
+                            qc[e] = base + 512 * T + 128 * quarter + 4 * lane;
                         }
                         qn += __popc(bal);
-                        Tcur++;
-                        __syncwarp();
+                    };
+                    for (; gi < nGloc; gi++) {
+                        const int grp = dsub + DPQ * gi;
+                        float xr[16];
+                        ks_tmem_ld16(tmem_q + (unsigned)(16 * grp), xr);
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            if (i >= i_res && !overflow) {
+                                tile(4 * grp + i, make_float4(xr[4 * i], xr[4 * i + 1], xr[4 * i + 2], xr[4 * i + 3]));
+                                if (qn >= 32 && !batch()) { overflow = true; i_res = i + 1; }
+                            }
+                        }
+                        if (overflow) break;
+                        i_res = 0;
                     }
+                    while (!overflow && qn > 0)
+                        if (!batch()) overflow = true;
                     if (overflow && lane == 0) s_overflow = 1;
                     ks_dsync();  // every drain warp is done or stopped at a full buffer
                     const bool again = *reinterpret_cast<volatile int *>(&s_overflow) != 0;
                     if (!again) break;
+                    KS_ACC(1, td);
                     select_now();
+                    KS_ACC(2, td);
+                    KS_CNT(5, 1);
                 }
             }
+            KS_ACC(1, td);
             // the snapshot has been read: hand TMEM back (and with it the message slot)
             ks_tc_fence_before();
             __syncwarp();
@@ -615,13 +818,14 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
             // evaluate what this panel added; tighten the bound while the buffer is reasonably full
             ks_dsync();
             {
-                const int cnt = min(*reinterpret_cast<volatile int *>(&s_cnt), q.cap);
-                if (cnt > q.cap / 2 && !(m.flags & KS_FLAG_ROW_END)) select_now();
+                const int cnt = min(*reinterpret_cast<volatile int *>(&s_cnt), KS_CAP);
+                if (cnt > KS_CAP / 2 && !(m.flags & KS_FLAG_ROW_END)) { select_now(); KS_CNT(5, 1); }
                 else { evaluate(cnt); ks_dsync(); }
             }
+            KS_ACC(3, td);
             if (m.flags & KS_FLAG_ROW_END) {
                 // ---- final selection and slab write (s_plus.h:443-450) ----
-                const int n_out = ks_select(cand, n_eval, q.k, tau, &s_live, dtid);
+                const int n_out = ks_select(cand, n_eval, q.k, tau, &s_live, s_wsum, &s_pivot, dtid);
                 const size_t o = (size_t)m.i_out * (size_t)q.k;
                 for (int j = dtid; j < q.k; j += KS_DT) {
                     int col = 0, row = 0;
@@ -642,8 +846,14 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
                 }
                 row_open = false;
                 ks_dsync();
+                KS_ACC(4, td);
             }
         }
+#if SPY_KS_TIMING
+        // drain warp 0 -> 16..22: [0] wait for a snapshot  [1] sweep  [2] selections forced by a full buffer  [3] evaluate / tighten
+        // [4] final selection + write  [5] selections  [6] per-slot batches
+        if (tid == 0) for (int i = 0; i < 7; i++) atomicAdd(q.phase + 16 + i, (u64)kt[i]);
+#endif
     }
     ks_tc_fence_before();
     __syncthreads();
@@ -660,7 +870,7 @@ struct StreamPlan {
     int W, n_panels, cap;
     size_t smem_bytes;
 };
-// false when the stream engine does not cover the configuration (k too large for the shared-memory budget)
+// false when the stream engine does not cover the configuration (k too large for its candidate buffer)
 bool stream_plan(int k, int n_cols, int panel_width, int max_smem_optin, StreamPlan &sp);
 int64_t stream_scratch_bytes(int n_cols);
 int stream_launch(const spy_knn_args &a, const StreamPlan &sp, int kind, int exact_only, int grid, void *scratch,

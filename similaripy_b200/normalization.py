@@ -95,6 +95,8 @@ def _device_rows(X: DeviceMatrix, axis: int, inplace: bool):
         s = transpose_csr(ctx, s)
     elif not inplace:
         s = DeviceCSR(s.n_rows, s.n_cols, s.indptr, s.indices, s.data.clone(), sorted_rows=s.sorted_rows)
+    else:
+        s.invalidate()  # values are about to be overwritten in place: prepared operands cached on the handle are stale
     return ctx, s, want_transposed
 
 
