@@ -143,7 +143,7 @@ typedef struct spy_knn_args {
 #define SPY_ENGINE_FLAT 1
 #define SPY_ENGINE_STREAM 2
 /* what SPY_ENGINE_AUTO resolves to when the configuration is covered by both */
-#define SPY_ENGINE_DEFAULT SPY_ENGINE_FLAT
+#define SPY_ENGINE_DEFAULT SPY_ENGINE_STREAM
 
 /* Choose panel_width / n_panels / split_stride / threads / group for a problem (device < 0: plan with B200
  * defaults without touching the CUDA runtime).  Fills the plan fields of *args. */

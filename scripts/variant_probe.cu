@@ -230,8 +230,8 @@ int main(int argc, char **argv) {
             CK(cudaMemcpy(ph, (char *)d_scratch + sb - 256, sizeof(ph), cudaMemcpyDeviceToHost));
             const char *names[24] = {"X snapshot", "X pass body", "X end-of-pass barrier", "X snapshot", "X wait drain", "X setup+first issue", "X passes", "",
                                      "S snapshot", "S staging", "S end-of-pass barrier", "S snapshot", "S wait drain", "S setup", "S passes", "",
-                                     "D wait snapshot", "D sweep", "D forced selections", "D evaluate/tighten", "D final select+write", "D selections", "D slot batches", ""};
-            for (int i = 0; i < 24; i++) if (names[i][0]) printf("    %-24s %12.3f Mcycles per CTA%s\n", names[i], ph[i] / 148.0 / 1e6, (i % 8 == 6 || i == 21) ? " (count, in millions)" : "");
+                                     "D wait snapshot", "D sweep", "D forced selections", "D evaluate/tighten", "D final select+write", "D selections", "D slot batches", "D failed speculations"};
+            for (int i = 0; i < 24; i++) if (names[i][0]) printf("    %-24s %12.3f Mcycles per CTA%s\n", names[i], ph[i] / 148.0 / 1e6, (i % 8 == 6 || i == 21 || i == 23) ? " (count, in millions)" : "");
         }
         printf("%-44s %8.3f ms  %7.1f Gprod/s  engine %d (tables %.2f ms) panels %d x %d  threads %d group %d   rows differing from the first library: %ld\n",
                argv[li], best, products / best / 1e6, a.engine, prep_ms, a.n_panels, a.panel_width, a.threads, a.group, bad_rows);

@@ -21,6 +21,9 @@ from . import sharded as _sharded
 # Reuse prepared operands across calls on the same DeviceMatrix (SIMILARIPY_B200_CACHE=0 switches it off)
 CACHE_OPERANDS = os.environ.get("SIMILARIPY_B200_CACHE", "1") != "0"
 
+# Defaults merged under every call's `tuning` (tests switch kernel generations with it): e.g. {"engine_prefer": "stream"}
+DEFAULT_TUNING: dict = {}
+
 # When set to a list, every hot-kernel launch appends {start, end (CUDA events), plan...} to it (bench.py).
 KERNEL_TRACE = None
 
@@ -571,9 +574,16 @@ class KnnJob:
         a.panel_width = int(self.tuning.get("panel_width", 0))
         a.group = int(self.tuning.get("group", 0))
         a.b_nnz = B.nnz
+        # "engine": that kernel generation or an error; "engine_prefer": that one when it covers the configuration
         eng = self.tuning.get("engine", 0)
-        a.engine = _lib.ENGINES[eng] if isinstance(eng, str) else int(eng)
-        _lib.check(lib.spy_knn_plan(C.byref(a), ctx.index))
+        prefer = self.tuning.get("engine_prefer") if not eng else None
+        want = prefer if prefer is not None else eng
+        a.engine = _lib.ENGINES[want] if isinstance(want, str) else int(want)
+        rc = lib.spy_knn_plan(C.byref(a), ctx.index)
+        if rc == _lib.ERR_UNSUPPORTED and prefer is not None:
+            a.engine = _lib.ENGINE_AUTO if _lib.ENGINES.get(prefer, prefer) == _lib.ENGINE_FLAT else _lib.ENGINE_FLAT
+            rc = lib.spy_knn_plan(C.byref(a), ctx.index)
+        _lib.check(rc)
         if a.n_panels > 1:
             # the panel split needs ascending columns inside every row of B (a sorted CLONE when it is not: the
             # caller's handle is never permuted)
@@ -758,7 +768,7 @@ def prepare_job(matrix1, matrix2=None, weight_depop_matrix1="none", weight_depop
     params = dict(a1=f32(a1), l1=f32(l1), l2=f32(l2), l3=f32(l3), t1=f32(t1), t2=f32(t2),
                   stabilized_shrink=f32(stabilized_shrink), bayesian_shrink=f32(bayesian_shrink), threshold=f32(threshold))
     job = KnnJob(ctx=ctx, A=A, B=B, targets=ctx.h2d(targets_np), n_targets=int(targets_np.shape[0]), k=k,
-                 n_rows=n_rows, n_cols=n_cols, params=params, unique_targets=unique, tuning=dict(tuning or {}),
+                 n_rows=n_rows, n_cols=n_cols, params=params, unique_targets=unique, tuning={**DEFAULT_TUNING, **dict(tuning or {})},
                  targets_key=("all", n_rows) if target_rows is None else None)
     job.build_vectors(weight_depop_matrix1, weight_depop_matrix2, f32(p1), f32(p2), f32(c1), f32(c2), f32(additive_shrink))
     job.build_selectors(filter_cols, target_cols, raw_b)

@@ -83,6 +83,7 @@ SIGNATURES = {
 
 ABI_VERSION = 5
 ENGINE_AUTO, ENGINE_FLAT, ENGINE_STREAM = 0, 1, 2
+ERR_UNSUPPORTED = -4
 ENGINES = {"auto": ENGINE_AUTO, "flat": ENGINE_FLAT, "stream": ENGINE_STREAM}
 _lib = None
 

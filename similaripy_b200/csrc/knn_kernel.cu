@@ -243,7 +243,7 @@ int64_t spy_knn_scratch_bytes(const spy_knn_args *args, int device) {
     if (!args) return SPY_ERR_INVALID;
     Plan pl;
     if (make_plan(*args, device, pl) != SPY_OK) return SPY_ERR_INVALID;
-    if (pl.engine == SPY_ENGINE_STREAM) return stream_scratch_bytes(args->n_cols);
+    if (pl.engine == SPY_ENGINE_STREAM) return stream_scratch_bytes(pl.n_panels);
     int64_t bytes = 256 + block_min_bytes(args->n_cols);  // work counter (+ phase counters), per-block minima of Y
     if (!pl.cand_smem) bytes += (int64_t)grid_size(pl, std::max(args->n_targets, 1), device) * pl.cap * 8;
     return bytes;

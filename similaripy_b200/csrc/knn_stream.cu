@@ -77,16 +77,16 @@ __global__ void build_aexp_kernel(int n_targets, const int *__restrict__ targets
     }
 }
 
-// out[b] = min of y over columns [128 b, 128 b + 128): the drain's coarse bound (one warp per block)
-__global__ void block_min128_kernel(int n, const float *__restrict__ y, float *__restrict__ out) {
-    const int lane = threadIdx.x & 31;
-    const int blk = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
-    if (blk * 128 >= n) return;
+// out[pn * 128 + l] = min of y over the columns TMEM lane l holds of panel pn: quads l, l + 128, ... of the panel's W
+// columns (the drain's coarse bound is one register per lane); +inf when the lane has no column inside the matrix
+__global__ void lane_min_kernel(int n_cols, int W, int n_panels, const float *__restrict__ y, float *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_panels * 128) return;
+    const int pn = i >> 7, l = i & 127;
     float m = __int_as_float(0x7f800000);
-    for (int i = blk * 128 + lane; i < min(n, blk * 128 + 128); i += 32) m = fminf(m, y[i]);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if (lane == 0) out[blk] = m;
+    for (int c0 = pn * W + 4 * l; c0 < min(n_cols, (pn + 1) * W); c0 += 512)
+        for (int c = c0; c < min(n_cols, c0 + 4); c++) m = fminf(m, y[c]);
+    out[i] = m;
 }
 
 bool stream_plan(int k, int n_cols, int panel_width, int max_smem_optin, StreamPlan &sp) {
@@ -109,8 +109,8 @@ bool stream_plan(int k, int n_cols, int panel_width, int max_smem_optin, StreamP
     return true;
 }
 
-static int64_t bm_bytes(int n_cols) { return (((int64_t)(std::max(n_cols, 1) + 127) / 128) * 4 + 255) / 256 * 256; }
-int64_t stream_scratch_bytes(int n_cols) { return 256 + 3 * bm_bytes(n_cols) + 256; }
+static int64_t lm_bytes(int n_panels) { return (int64_t)std::max(n_panels, 1) * 128 * 4; }
+int64_t stream_scratch_bytes(int n_panels) { return 256 + 3 * lm_bytes(n_panels) + 256; }
 
 template <int KIND>
 static knn_stream_kernel_t stream_kernel() { return (knn_stream_kernel_t)knn_stream_kernel<KIND>; }
@@ -120,7 +120,7 @@ int stream_launch(const spy_knn_args &a, const StreamPlan &sp, int kind, int exa
     SPY_REQUIRE(a.b_chunks && a.b_chunk_indptr && a.toff, "stream engine: b_chunks / b_chunk_indptr / toff missing");
     SPY_REQUIRE(a.n_entries == 0 || a.aexp, "stream engine: aexp missing (spy_knn_build_aexp_dev)");
     SPY_REQUIRE(a.target_mode != SPY_SEL_MATRIX && !exact_only, "stream engine does not cover this configuration");
-    SPY_REQUIRE(scratch != nullptr && scratch_bytes >= stream_scratch_bytes(a.n_cols), "scratch too small");
+    SPY_REQUIRE(scratch != nullptr && scratch_bytes >= stream_scratch_bytes(sp.n_panels), "scratch too small");
     KnnStreamDev p;
     KnnDev &d = p.q;
     d.n_targets = a.n_targets; d.targets = a.targets; d.row_order = a.row_order;
@@ -140,7 +140,7 @@ int stream_launch(const spy_knn_args &a, const StreamPlan &sp, int kind, int exa
     d.out_rows = a.out_rows; d.out_cols = a.out_cols; d.out_vals = a.out_values; d.out_counts = a.out_counts;
     unsigned char *sc = reinterpret_cast<unsigned char *>(scratch);
     d.work_counter = reinterpret_cast<int *>(sc);
-    d.phase = reinterpret_cast<u64 *>(sc + 256 + 3 * bm_bytes(a.n_cols));  // SPY_KS_TIMING builds: 24 counters
+    d.phase = reinterpret_cast<u64 *>(sc + 256 + 3 * lm_bytes(sp.n_panels));  // SPY_KS_TIMING builds: 24 counters
     d.cand_global = nullptr;
     p.err = reinterpret_cast<int *>(sc + 64);
     p.toff = reinterpret_cast<const long long *>(a.toff);
@@ -148,19 +148,18 @@ int stream_launch(const spy_knn_args &a, const StreamPlan &sp, int kind, int exa
     p.aexp = reinterpret_cast<const uint2 *>(a.aexp);
     p.chunks = reinterpret_cast<const uint4 *>(a.b_chunks);
     SPY_CUDA_OK(cudaMemsetAsync(scratch, 0, 256, st));
-    SPY_CUDA_OK(cudaMemsetAsync(sc + 256 + 3 * bm_bytes(a.n_cols), 0, 256, st));
-    // per-128-column minima of the Y vectors in use: the drain's coarse bound
-    const int64_t bmb = bm_bytes(a.n_cols);
-    const int blocks = (std::max(a.n_cols, 1) + 127) / 128;
+    SPY_CUDA_OK(cudaMemsetAsync(sc + 256 + 3 * lm_bytes(sp.n_panels), 0, 256, st));
+    // minima of the Y vectors in use over the columns every TMEM lane holds of every panel: the drain's coarse bound
+    const int64_t lmb = lm_bytes(sp.n_panels);
     p.ymin_t = p.ymin_c = p.ymin_d = nullptr;
     const float *src[3] = {a.l1 != 0.f ? a.Ytversky : nullptr, a.l2 != 0.f ? a.Ycosine : nullptr, a.l3 != 0.f ? a.Ydepop : nullptr};
     const float **dst[3] = {&p.ymin_t, &p.ymin_c, &p.ymin_d};
     for (int i = 0; i < 3; i++) {
         if (src[i] == nullptr || a.n_cols <= 0) continue;
-        float *bm = reinterpret_cast<float *>(sc + 256 + i * bmb);
-        block_min128_kernel<<<(blocks * 32 + 255) / 256, 256, 0, st>>>(a.n_cols, src[i], bm);
+        float *lm = reinterpret_cast<float *>(sc + 256 + i * lmb);
+        lane_min_kernel<<<(sp.n_panels * 128 + 127) / 128, 128, 0, st>>>(a.n_cols, sp.W, sp.n_panels, src[i], lm);
         SPY_LAUNCH_OK();
-        *dst[i] = bm;
+        *dst[i] = lm;
     }
     knn_stream_kernel_t kern;
     switch (kind) {

@@ -39,18 +39,25 @@ struct KnnStreamDev {
     long long E;             // toff[n_targets]
     const uint2 *aexp;       // [n_panels][E]: (first chunk, end chunk) of the entry's B-row segment inside the panel
     const uint4 *chunks;     // B as 16-byte chunks of two (column, value) pairs; every row padded to whole chunks
-    const float *ymin_t, *ymin_c, *ymin_d;  // minima of Yt / Yc / Yd over every 128 consecutive columns (NULL: unused)
+    const float *ymin_t, *ymin_c, *ymin_d;  // [n_panels][128]: minimum of Yt / Yc / Yd over the columns a TMEM lane holds of a panel
+                                            // (quads lane, lane + 128, ... of the panel); NULL: unused
     int *err;                // set to non-zero before a trap (bounded waits)
 };
 
 #ifndef SPY_KS_D_WARPS
-#define SPY_KS_D_WARPS 4
+#define SPY_KS_D_WARPS 8
 #endif
 #ifndef SPY_KS_U
 #define SPY_KS_U 2
 #endif
+#ifndef SPY_KS_RING
+#define SPY_KS_RING 1  // 1: cp.async (LDGSTS) ring in shared memory; 0: the next batch waits in registers (LDG.128)
+#endif
+#ifndef SPY_KS_SPEC
+#define SPY_KS_SPEC 1  // speculative bound for a row's first panel (validated; see the drain)
+#endif
 #ifndef SPY_KS_PREFETCH
-#define SPY_KS_PREFETCH 1
+#define SPY_KS_PREFETCH 0  // bulk L2 prefetch of the next pass's segments: measured slower (43.1 vs 40.4 ms, profiles/r02)
 #endif
 constexpr int KS_NT = 1024;
 constexpr int KS_D_WARPS = SPY_KS_D_WARPS;     // warps 0..D-1: drain (4 or 8: whole lane quarters)
@@ -79,7 +86,7 @@ struct KsMsg {    // what the expansion side hands to the drain with every snaps
     int t, i_out, pn, flags, landed;
 };
 
-__host__ __device__ constexpr size_t ks_ring_bytes() { return (size_t)KS_A_WARPS * 32 * KS_U * 16; }
+__host__ __device__ constexpr size_t ks_ring_bytes() { return SPY_KS_RING ? (size_t)KS_A_WARPS * 32 * KS_U * 16 : 0; }
 __host__ __device__ constexpr size_t ks_stage_bytes() { return (size_t)2 * (3 * KS_CH * 4 + 32 * 4); }
 __host__ __device__ constexpr size_t ks_queue_bytes() { return (size_t)KS_D_WARPS * KS_QCAP * (16 + 4); }
 __host__ __device__ constexpr size_t ks_fixed_bytes() { return ks_ring_bytes() + ks_stage_bytes() + ks_queue_bytes() + (size_t)KS_CAP * 8; }
@@ -412,6 +419,11 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
         const unsigned *cP = nullptr;  // staged pass: prefixes; first chunks at + KS_CH, values at + 2 KS_CH
         float vp[KS_U];
         unsigned lp = 0u;
+#if !SPY_KS_RING
+        uint4 nx[KS_U];  // the batch in flight
+#pragma unroll
+        for (int r = 0; r < KS_U; r++) nx[r] = make_uint4(0u, 0u, 0u, 0u);
+#endif
 #pragma unroll
         for (int r = 0; r < KS_U; r++) vp[r] = 0.f;
         auto prefix_at = [&](int idx) -> unsigned {  // chunks of the pass before segment idx (all lanes call it together)
@@ -442,11 +454,17 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
                 const unsigned pe = __shfl_sync(0xffffffffu, Pe, j), c0 = __shfl_sync(0xffffffffu, C0, j);
                 vp[r] = __shfl_sync(0xffffffffu, V, j);
                 if (live) {
+#if SPY_KS_RING
                     ks_cp_async16(slot32 + (unsigned)r * 512u, p.chunks + (c0 + (fr - pe)));
+#else
+                    nx[r] = __ldg(p.chunks + (c0 + (fr - pe)));
+#endif
                     lp |= 1u << r;
                 }
             }
+#if SPY_KS_RING
             ks_cp_commit();
+#endif
             f = min(f + 32u * KS_U, fb);
         };
 
@@ -558,11 +576,16 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
             KS_ACC(0, tp);  // (the snapshot, also counted in [3] / [4])
             const bool any = have;
             while (have) {
-                ks_cp_wait_all();
                 uint4 pr[KS_U];
                 float vc[KS_U];
+#if SPY_KS_RING
+                ks_cp_wait_all();
 #pragma unroll
                 for (int r = 0; r < KS_U; r++) { pr[r] = ks_lds128u(slot32 + (unsigned)r * 512u); vc[r] = vp[r]; }
+#else
+#pragma unroll
+                for (int r = 0; r < KS_U; r++) { pr[r] = nx[r]; vc[r] = vp[r]; }
+#endif
                 const unsigned lc = lp;
                 const bool more = f < F1;
                 if (more) issue();
@@ -684,29 +707,31 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
             if (m.landed) {
 #endif
                 const int base = m.pn * q.W;
+                // One sweep over this warp's share of the snapshot.  lo_s: an extra (speculative) lower bound; sample: only ONE
+                // pseudo-randomly chosen tile, every touched slot of it (see the speculative bound below).
+                auto sweep = [&](float lo_s, bool sample) {
                 int gi = 0, i_res = 0, qn = 0;  // next group of four tiles of this warp's sweep, first tile of it still to do; queued quads
-                for (;;) {  // sweep; leaves the loop when the warp's share is done; re-entered after an overflow
+                for (;;) {  // leaves the loop when the warp's share is done; re-entered after an overflow
                     bool overflow = false;
-                    // coarse bound of a tile (per 128-column block of this warp's lane quarter): a slot can only enter the
-                    // result if  x >= lo * den  and  den >= Dmin + cX * x  with Dmin from the block minima of Y, i.e.
-                    // x * (1 - lo * cX) >= lo * Dmin.  Lane l holds the bounds of tiles l, l + 32, l + 64, l + 96.
-                    const float g = 1.f - lo * fr.cX;
-                    const bool coarse = filter && lo > 0.f && g > 0.f && fr.cT >= 0.f && fr.cC >= 0.f && fr.cD >= 0.f &&
+                    const float lo_u = fmaxf(lo, lo_s);  // (lo itself rises when a full buffer forces a selection)
+                    const bool flt = filter && !sample;
+                    // coarse bound of THIS LANE's slots of the panel (it holds quads lane, lane + 128, ... of its quarter): a slot
+                    // can only enter the result if  x >= lo * den  and  den >= Dmin + cX * x  with Dmin from the minima of Y over
+                    // the lane's columns, i.e.  x * (1 - lo * cX) >= lo * Dmin.  A register per lane: the sweep below needs no
+                    // shuffle and no shared memory per tile (the shared-memory pipe is saturated by the expansion's adds).
+                    const float g = 1.f - lo_u * fr.cX;
+                    const bool coarse = flt && lo_u > 0.f && g > 0.f && fr.cT >= 0.f && fr.cC >= 0.f && fr.cD >= 0.f &&
                                         (!useT || p.ymin_t != nullptr) && (!useC || p.ymin_c != nullptr) && (!useD || p.ymin_d != nullptr);
-                    float cb0 = 0.f, cb1 = 0.f, cb2 = 0.f, cb3 = 0.f;
+                    float bound = 0.f;
                     if (coarse) {
-                        auto tile_bound = [&](int T) -> float {
-                            const int blk = (base >> 7) + 4 * T + quarter;
-                            if (T >= nT || blk >= ((q.n_cols + 127) >> 7)) return 0.f;
-                            float dmin = fr.A0;
-                            if (useT) dmin = fmaf(fr.cT, __ldg(p.ymin_t + blk), dmin);
-                            if (useC) dmin = fmaf(fr.cC, __ldg(p.ymin_c + blk), dmin);
-                            if (useD) dmin = fmaf(fr.cD, __ldg(p.ymin_d + blk), dmin);
-                            return (KIND == KIND_RAW) ? lo : (dmin > 0.f ? lo * dmin / g : 0.f);
-                        };
-                        cb0 = tile_bound(lane); cb1 = tile_bound(lane + 32); cb2 = tile_bound(lane + 64); cb3 = tile_bound(lane + 96);
+                        const int li = m.pn * 128 + quarter * 32 + lane;
+                        float dmin = fr.A0;
+                        if (useT) dmin = fmaf(fr.cT, __ldg(p.ymin_t + li), dmin);
+                        if (useC) dmin = fmaf(fr.cC, __ldg(p.ymin_c + li), dmin);
+                        if (useD) dmin = fmaf(fr.cD, __ldg(p.ymin_d + li), dmin);
+                        bound = (KIND == KIND_RAW) ? lo_u : (dmin > 0.f ? lo_u * dmin / g : 0.f);
                     }
-                    const float lc = lo * (KIND == KIND_D ? fr.cD : fr.cC), la = lo * fr.A0;
+                    const float lc = lo_u * (KIND == KIND_D ? fr.cD : fr.cC), la = lo_u * fr.A0;
                     // per-slot test of up to 32 queued quads, all lanes busy: one L2 round trip for the batch; false = buffer full
                     auto batch = [&]() -> bool {
                         __syncwarp();
@@ -727,7 +752,7 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
                                 if (useC) yc = load_y4(q.Yc, col0, q.n_cols);
                                 if (useD) yd = load_y4(q.Yd, col0, q.n_cols);
                             }
-                            sm = survivor_mask<KIND>(q, fr, filter, lo, lc, la, x, yt, yc, yd);
+                            sm = survivor_mask<KIND>(q, fr, flt, lo_u, lc, la, x, yt, yc, yd);
                         }
                         const int c = __popc(sm);
                         int inc = c;
@@ -757,24 +782,15 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
                     };
                     // coarse test of one tile: quads that cannot be rejected as a whole join the queue
                     auto tile = [&](int T, const float4 x) {
-                        bool pass;
-                        if (coarse) {
-                            const int ri = T >> 5;
-                            const float mine = ri == 0 ? cb0 : ri == 1 ? cb1 : ri == 2 ? cb2 : cb3;
-                            const float bound = __shfl_sync(0xffffffffu, mine, T & 31);
-                            // (an untouched slot holds -0.0f: it fails x >= bound for every bound > 0)
-                            pass = (x.x >= bound) | (x.y >= bound) | (x.z >= bound) | (x.w >= bound);
-                            if (bound <= 0.f || !(KIND == KIND_RAW || KIND == KIND_C || KIND == KIND_D)) {
-                                // no usable bound for the block: every touched slot goes on; and where the denominator may be
-                                // negative a negative dot product is left to the per-slot test
-                                const bool touched = (__float_as_uint(x.x) != kSentinelBits) | (__float_as_uint(x.y) != kSentinelBits) |
-                                                     (__float_as_uint(x.z) != kSentinelBits) | (__float_as_uint(x.w) != kSentinelBits);
-                                if (bound <= 0.f) pass = touched;
-                                else pass = (pass | (x.x < 0.f) | (x.y < 0.f) | (x.z < 0.f) | (x.w < 0.f)) & touched;
-                            }
-                        } else {
-                            pass = (__float_as_uint(x.x) != kSentinelBits) | (__float_as_uint(x.y) != kSentinelBits) |
-                                   (__float_as_uint(x.z) != kSentinelBits) | (__float_as_uint(x.w) != kSentinelBits);
+                        // (an untouched slot holds -0.0f: it fails x >= bound for every bound > 0)
+                        bool pass = (x.x >= bound) | (x.y >= bound) | (x.z >= bound) | (x.w >= bound);
+                        if (bound <= 0.f || !(KIND == KIND_RAW || KIND == KIND_C || KIND == KIND_D)) {
+                            // no usable bound for the lane: every touched slot goes on; and where the denominator may be negative
+                            // a negative dot product is left to the per-slot test
+                            const bool touched = (__float_as_uint(x.x) != kSentinelBits) | (__float_as_uint(x.y) != kSentinelBits) |
+                                                 (__float_as_uint(x.z) != kSentinelBits) | (__float_as_uint(x.w) != kSentinelBits);
+                            if (bound <= 0.f) pass = touched;
+                            else pass = (pass | (x.x < 0.f) | (x.y < 0.f) | (x.z < 0.f) | (x.w < 0.f)) & touched;
                         }
                         const unsigned bal = __ballot_sync(0xffffffffu, pass);
                         if (pass) {
@@ -784,7 +800,22 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
                         }
                         qn += __popc(bal);
                     };
-                    for (; gi < nGloc; gi++) {
+                    while (!overflow && qn >= 32)  // (a round that follows an overflow starts with a full queue)
+                        if (!batch()) overflow = true;
+                    if (sample) {
+                        if (gi == 0) {  // tile (h % nGloc, (h >> 16) % 4) of this warp's share: spread over the panel, different per row
+                            unsigned h = (unsigned)m.t * 0x9E3779B1u + (unsigned)warp * 0x85EBCA6Bu;
+                            h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12;
+                            const int grp = dsub + DPQ * (int)(h % (unsigned)nGloc), i = (int)((h >> 16) & 3u);
+                            float xr[16];
+                            ks_tmem_ld16(tmem_q + (unsigned)(16 * grp), xr);
+                            const float4 x = i == 0 ? make_float4(xr[0], xr[1], xr[2], xr[3]) : i == 1 ? make_float4(xr[4], xr[5], xr[6], xr[7])
+                                           : i == 2 ? make_float4(xr[8], xr[9], xr[10], xr[11]) : make_float4(xr[12], xr[13], xr[14], xr[15]);
+                            tile(4 * grp + i, x);
+                            gi = 1;
+                        }
+                    } else
+                    for (; gi < nGloc && !overflow; gi++) {
                         const int grp = dsub + DPQ * gi;
                         float xr[16];
                         ks_tmem_ld16(tmem_q + (unsigned)(16 * grp), xr);
@@ -809,6 +840,56 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
                     KS_ACC(2, td);
                     KS_CNT(5, 1);
                 }
+                };
+                // ---- speculative bound for a row that has none yet (its first non-empty panel) ----
+                // Without a bound the sweep floods the candidate buffer and two or three selections are forced before the
+                // pre-filter bites.  Instead: SAMPLE one tile per drain warp (every touched slot of it), take the r-th best
+                // sample as the bound -- r chosen so that the panel holds k candidates above it with overwhelming probability --
+                // and sweep with it.  The snapshot is read-only, so the bound is simply VALIDATED afterwards (k buffered
+                // candidates beat it) and the panel swept again without it if it is not: results never depend on the sample.
+                bool done = false;
+                if (SPY_KS_SPEC && filter && tau == 0ull && n_eval == 0 && nG >= 2 * DPQ) {  // (uniform over the drain warps)
+                    sweep(0.f, true);
+                    const int cnt = min(*reinterpret_cast<volatile int *>(&s_cnt), KS_CAP);
+                    evaluate(cnt);
+                    ks_dsync();
+                    const int width = min(q.W, q.n_cols - base);
+                    const float f = (float)(KS_D_WARPS * 128) / (float)max(width, 1), kf = (float)q.k * f;
+#ifdef SPY_SPEC_FORCE_RANK  // test builds: a bound that is almost never valid, to exercise the re-sweep
+                    const int r_s = SPY_SPEC_FORCE_RANK;
+#else
+                    const int r_s = (int)ceilf(kf + 3.5f * sqrtf(kf) + 1.5f);
+#endif
+                    u64 tau_s = 0ull;
+                    const bool usable = f < 0.4f && cnt >= 8 * r_s;  // uniform
+                    if (usable && ks_select(cand, cnt, r_s, tau_s, &s_live, s_wsum, &s_pivot, dtid) < r_s) tau_s = 0ull;
+                    ks_dsync();
+                    if (dtid == 0) s_cnt = 0;  // the sample was only read: its slots are all still in the snapshot
+                    n_eval = 0;
+                    ks_dsync();
+                    if (tau_s != 0ull) {
+                        sweep(reject_bound(q, tau_s), false);
+                        const int c2 = min(*reinterpret_cast<volatile int *>(&s_cnt), KS_CAP);
+                        evaluate(c2);
+                        if (dtid == 0) s_live = 0;
+                        ks_dsync();
+                        int above = 0;
+                        for (int i = dtid; i < c2; i += KS_DT) above += cand[i] > tau_s ? 1 : 0;
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) above += __shfl_xor_sync(0xffffffffu, above, o);
+                        if (lane == 0 && above) atomicAdd(&s_live, above);
+                        ks_dsync();
+                        done = *reinterpret_cast<volatile int *>(&s_live) >= q.k;
+                        ks_dsync();
+                        KS_CNT(7, done ? 0 : 1);
+                        if (!done) {  // not validated: forget what was buffered, sweep again with the valid bound (none)
+                            if (dtid == 0) s_cnt = 0;
+                            n_eval = 0; tau = 0ull; lo = reject_bound(q, tau);
+                            ks_dsync();
+                        }
+                    }
+                }
+                if (!done) sweep(0.f, false);
             }
             KS_ACC(1, td);
             // the snapshot has been read: hand TMEM back (and with it the message slot)
@@ -852,7 +933,7 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
 #if SPY_KS_TIMING
         // drain warp 0 -> 16..22: [0] wait for a snapshot  [1] sweep  [2] selections forced by a full buffer  [3] evaluate / tighten
         // [4] final selection + write  [5] selections  [6] per-slot batches
-        if (tid == 0) for (int i = 0; i < 7; i++) atomicAdd(q.phase + 16 + i, (u64)kt[i]);
+        if (tid == 0) for (int i = 0; i < 8; i++) atomicAdd(q.phase + 16 + i, (u64)kt[i]);  // [7] speculative bounds that failed validation
 #endif
     }
     ks_tc_fence_before();
@@ -872,7 +953,7 @@ struct StreamPlan {
 };
 // false when the stream engine does not cover the configuration (k too large for its candidate buffer)
 bool stream_plan(int k, int n_cols, int panel_width, int max_smem_optin, StreamPlan &sp);
-int64_t stream_scratch_bytes(int n_cols);
+int64_t stream_scratch_bytes(int n_panels);
 int stream_launch(const spy_knn_args &a, const StreamPlan &sp, int kind, int exact_only, int grid, void *scratch,
                   int64_t scratch_bytes, cudaStream_t st);
 }  // namespace spy

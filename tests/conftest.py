@@ -28,3 +28,20 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+# ---- both kernel generations: modules that list the `spy_engine` fixture run every test with the flat engine and with
+#      the stream engine preferred (configurations the stream engine does not cover fall back to the flat one) ----
+def pytest_generate_tests(metafunc):
+    if "spy_engine" in metafunc.fixturenames:
+        metafunc.parametrize("spy_engine", ["flat", "stream"], indirect=True)
+
+
+@pytest.fixture
+def spy_engine(request):
+    from similaripy_b200 import _engine
+    saved = dict(_engine.DEFAULT_TUNING)
+    _engine.DEFAULT_TUNING["engine_prefer"] = request.param
+    yield request.param
+    _engine.DEFAULT_TUNING.clear()
+    _engine.DEFAULT_TUNING.update(saved)

@@ -1,0 +1,54 @@
+"""CPU: bench.py's synthetic generator builds the same bits with numpy (reference arm) and with torch (GPU arm; run
+on the CPU device here), and the planner resolves the kernel generations as documented."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import bench
+
+
+@pytest.mark.parametrize("shape", [(5000, 3000, 0.01, 7), (300, 50, 0.2, 2), (1000, 2000, 0.025, 0)])
+def test_host_and_device_generators_are_bit_identical(shape):
+    import torch
+    n_rows, n_cols, density, seed = shape
+    m = bench.gen_urm_host(n_rows, n_cols, density, seed)
+    ip, ix, dv = bench.gen_urm_device(n_rows, n_cols, density, seed, torch.device("cpu"))
+    assert np.array_equal(m.indptr, ip.numpy()) and np.array_equal(m.indices, ix.numpy())
+    assert np.array_equal(m.data, dv.numpy()) and m.data.dtype == np.float32
+    assert m.data.min() > 0.0 and m.data.max() <= 1.0
+    # rows: distinct ascending columns, nnz close to n_rows * n_cols * density
+    for r in (0, n_rows // 2, n_rows - 1):
+        row = m.indices[m.indptr[r]: m.indptr[r + 1]]
+        assert np.all(np.diff(row) > 0)
+    assert abs(m.nnz / (n_rows * n_cols * density) - 1.0) < 0.1
+
+
+def test_engine_resolution_in_the_planner():
+    from similaripy_b200 import _lib
+    lib = _lib.load()
+
+    def plan(**kw):
+        a = _lib.KnnArgs()
+        a.k, a.n_cols, a.n_targets, a.a1 = 100, 200_000, 1000, 1.0
+        for k, v in kw.items():
+            setattr(a, k, v)
+        return lib.spy_knn_plan(ctypes.byref(a), -1), a
+
+    rc, a = plan(engine=_lib.ENGINE_STREAM)
+    assert rc == 0 and a.engine == _lib.ENGINE_STREAM and a.panel_width % 2048 == 0 and a.threads == 1024
+    assert a.panel_width * a.n_panels >= 200_000 and a.panel_width <= 65536
+    rc, a = plan(engine=_lib.ENGINE_FLAT)
+    assert rc == 0 and a.engine == _lib.ENGINE_FLAT and a.panel_width % 128 == 0
+    rc, a = plan()  # auto resolves to one of the two
+    assert rc == 0 and a.engine in (_lib.ENGINE_FLAT, _lib.ENGINE_STREAM)
+    # what the stream engine does not cover is refused when asked for explicitly ...
+    for kw in (dict(target_mode=_lib.SEL_MATRIX), dict(a1=0.5), dict(bayesian_shrink=1.0), dict(k=600), dict(threads=512)):
+        rc, _ = plan(engine=_lib.ENGINE_STREAM, **kw)
+        assert rc == _lib.ERR_UNSUPPORTED, kw
+        rc, a = plan(**kw)  # ... and takes the flat engine on its own
+        assert rc == 0 and a.engine == _lib.ENGINE_FLAT, kw
+    rc, _ = plan(engine=7)
+    assert rc < 0
+    rc, _ = plan(threads=768)  # experiment builds only
+    assert rc < 0 and b"threads must be" in lib.spy_last_error()

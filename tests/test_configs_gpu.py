@@ -8,7 +8,7 @@ respected, agreement between different launch plans), and for cfg2 (c) spot rows
 import numpy as np
 import pytest
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("spy_engine")]
 
 
 def _gen(n_rows, n_cols, density, seed):

@@ -1,6 +1,7 @@
 """GPU: the reference's OWN unit tests (tests/reference_fixtures/, unmodified copies of the upstream
 tests/test_similarity.py:289-617 and tests/test_normalization.py:12-96) run against similaripy_b200 with
 ``import similaripy`` resolved to this package -- the drop-in claim of SURVEY.md 8b, checked literally."""
+import contextlib
 import importlib.util
 import os
 import sys
@@ -9,11 +10,12 @@ import pytest
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 FIXTURES = os.path.join(HERE, "reference_fixtures")
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("spy_engine")]
 
 
-def _load(name):
-    """Import a fixture file with `similaripy` aliased to similaripy_b200; returns (module, restore)."""
+@contextlib.contextmanager
+def _aliased():
+    """`import similaripy` (also inside the fixtures' test bodies, e.g. test_example_code) resolves to similaripy_b200."""
     import similaripy_b200
     import similaripy_b200.cython_code
     import similaripy_b200.cython_code.utils
@@ -25,15 +27,20 @@ def _load(name):
     saved = {k: sys.modules.get(k) for k in alias}
     sys.modules.update(alias)
     try:
-        spec = importlib.util.spec_from_file_location(f"_ref_fixture_{name}", os.path.join(FIXTURES, name + ".py"))
-        mod = importlib.util.module_from_spec(spec)
-        spec.loader.exec_module(mod)
+        yield
     finally:
         for k, v in saved.items():
             if v is None:
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+def _load(name):
+    with _aliased():
+        spec = importlib.util.spec_from_file_location(f"_ref_fixture_{name}", os.path.join(FIXTURES, name + ".py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
     return mod
 
 
@@ -54,7 +61,8 @@ _MODULES = {}
 def test_reference_test(module, test):
     if module not in _MODULES:
         _MODULES[module] = _load(module)
-    getattr(_MODULES[module], test)()
+    with _aliased():
+        getattr(_MODULES[module], test)()
 
 
 def test_all_sixteen_reference_tests_are_covered():

@@ -9,7 +9,7 @@ import similaripy_b200 as sim
 from oracle import oracle
 from parity import assert_topk_parity, check_sum, random_csr
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("spy_engine")]
 
 PRESETS = [
     ("dot_product", {}),
