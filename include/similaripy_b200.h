@@ -137,6 +137,8 @@ typedef struct spy_knn_args {
     int64_t n_entries;          /* toff[n_targets]: stored entries of A in the target rows                    */
     const void *aexp;           /* [n_panels][n_entries] (first chunk, end chunk) of every (entry, panel):
                                  * spy_knn_build_aexp_dev                                                     */
+    int64_t a_nnz;              /* stored entries of A (0 = unknown): with b_nnz the planner estimates the scalar
+                                 * products per (target row, panel) and keeps short rows on the flat engine       */
 } spy_knn_args;
 
 #define SPY_ENGINE_AUTO 0
@@ -189,6 +191,14 @@ int spy_knn_topk_dev(const spy_knn_args *args, void *scratch, int64_t scratch_by
  * s_plus.pyx:359-384): uploads, plans, runs, downloads.  out_rows/out_cols/out_values are
  * host arrays of n_targets*k entries. */
 int spy_knn_topk_host(const spy_knn_args *host_args, int device);
+
+/* The same call over several GPUs of one box from one process: the target rows are cut into
+ * n_devices contiguous ranges of equal work (stored entries of A), every range runs on its device from its own host
+ * thread, B is replicated.  The caller's slab is the complete result in target order (assemble is accepted for
+ * symmetry with the torch.distributed path, similaripy_b200/sharded.py, where gathering is optional); range_bounds
+ * (n_devices + 1 entries, may be NULL) receives the cut positions.  The reference has one OpenMP loop (s_plus.h:313-338). */
+int spy_knn_topk_multi_host(const spy_knn_args *host_args, const int32_t *devices, int32_t n_devices, int32_t assemble,
+                            int32_t *range_bounds);
 
 /* work[i] = number of scalar products the expansion of target row i performs,
  * sum over u in A[targets[i],:] of nnz(B[u,:]).  The reference balances rows over threads with
@@ -271,6 +281,15 @@ int spy_tfidf_dev(int64_t n_rows, int64_t n_cols, void *data, int val_dtype, con
 int spy_bm25plus_dev(int64_t n_rows, int64_t n_cols, void *data, int val_dtype, const void *indices,
                      const void *indptr, int idx_dtype, double k1, double b, double delta,
                      int tf_mode, int idf_mode, double logbase, void *scratch, void *stream);
+
+/* The same three with HOST pointers: exactly the arguments of the reference's Cython functions
+ * inplace_normalize_csr_{l1,l2,max} / _tfidf / _bm25plus (normalization.pyx:97-102, 200-208, 260-271) -- the data,
+ * indices and indptr arrays of a scipy CSR matrix; `data` is overwritten in place. */
+int spy_normalize_rows_host(int norm, int64_t n_rows, void *data, int val_dtype, const void *indptr, int idx_dtype, int device);
+int spy_tfidf_host(int64_t n_rows, int64_t n_cols, void *data, int val_dtype, const void *indices, const void *indptr,
+                   int idx_dtype, int tf_mode, int idf_mode, double logbase, int device);
+int spy_bm25plus_host(int64_t n_rows, int64_t n_cols, void *data, int val_dtype, const void *indices, const void *indptr,
+                      int idx_dtype, double k1, double b, double delta, int tf_mode, int idf_mode, double logbase, int device);
 
 #ifdef __cplusplus
 }

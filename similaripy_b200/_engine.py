@@ -574,6 +574,7 @@ class KnnJob:
         a.panel_width = int(self.tuning.get("panel_width", 0))
         a.group = int(self.tuning.get("group", 0))
         a.b_nnz = B.nnz
+        a.a_nnz = A.nnz
         # "engine": that kernel generation or an error; "engine_prefer": that one when it covers the configuration
         eng = self.tuning.get("engine", 0)
         prefer = self.tuning.get("engine_prefer") if not eng else None

@@ -38,7 +38,7 @@ class KnnArgs(C.Structure):
         ("panel_width", _i32), ("b_split", _vp), ("split_stride", _i32), ("n_panels", _i32),
         ("threads", _i32), ("b_pairs", _vp), ("row_order", _vp),
         ("b_nnz", _i64), ("group", _i32),
-        ("engine", _i32), ("b_chunk_indptr", _vp), ("b_chunks", _vp), ("toff", _vp), ("n_entries", _i64), ("aexp", _vp),
+        ("engine", _i32), ("b_chunk_indptr", _vp), ("b_chunks", _vp), ("toff", _vp), ("n_entries", _i64), ("aexp", _vp), ("a_nnz", _i64),
     ]
 
 
@@ -59,6 +59,10 @@ SIGNATURES = {
     "spy_knn_build_aexp_dev": (C.c_int, [C.POINTER(KnnArgs), _vp]),
     "spy_knn_topk_dev": (C.c_int, [C.POINTER(KnnArgs), _vp, _i64, _vp]),
     "spy_knn_topk_host": (C.c_int, [C.POINTER(KnnArgs), C.c_int]),
+    "spy_knn_topk_multi_host": (C.c_int, [C.POINTER(KnnArgs), _vp, _i32, _i32, _vp]),
+    "spy_normalize_rows_host": (C.c_int, [C.c_int, _i64, _vp, C.c_int, _vp, C.c_int, C.c_int]),
+    "spy_tfidf_host": (C.c_int, [_i64, _i64, _vp, C.c_int, _vp, _vp, C.c_int, C.c_int, C.c_int, _f64, C.c_int]),
+    "spy_bm25plus_host": (C.c_int, [_i64, _i64, _vp, C.c_int, _vp, _vp, C.c_int, _f64, _f64, _f64, C.c_int, C.c_int, _f64, C.c_int]),
     "spy_csr_row_sum_dev": (C.c_int, [_i32, _vp, _vp, C.c_int, _vp, _vp]),
     "spy_csr_col_sum_dev": (C.c_int, [_i64, _vp, _vp, C.c_int, _i32, _vp, _vp, _vp]),
     "spy_pow_shift_dev": (C.c_int, [_i64, _vp, C.c_int, _f32, _f32, _vp, _vp]),

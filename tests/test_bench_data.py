@@ -48,6 +48,11 @@ def test_engine_resolution_in_the_planner():
         assert rc == _lib.ERR_UNSUPPORTED, kw
         rc, a = plan(**kw)  # ... and takes the flat engine on its own
         assert rc == 0 and a.engine == _lib.ENGINE_FLAT, kw
+    # short rows stay on the flat engine when the planner knows the operand sizes (configs[4]: 200 x 100 products per row)
+    rc, a = plan(a_rows=5_000_000, a_nnz=1_000_000_000, b_rows=200_000, b_nnz=20_000_000)
+    assert rc == 0 and a.engine == _lib.ENGINE_FLAT
+    rc, a = plan(a_rows=200_000, a_nnz=200_000_000, b_rows=1_000_000, b_nnz=200_000_000)  # configs[1]: 2e5 products per row
+    assert rc == 0 and a.engine == _lib.ENGINE_STREAM
     rc, _ = plan(engine=7)
     assert rc < 0
     rc, _ = plan(threads=768)  # experiment builds only

@@ -21,7 +21,8 @@ def _ptr(a):
     return None if a is None or a.size == 0 else a.ctypes.data_as(C.c_void_p)
 
 
-def _host_call(targets, A, B, vecs, scal, k, filt=None, targ=None, threads=0, panel_width=0, with_rows=True):
+def _host_call(targets, A, B, vecs, scal, k, filt=None, targ=None, threads=0, panel_width=0, with_rows=True, engine=0,
+               devices=None):
     """Fill struct spy_knn_args with host pointers and call the library; returns the slab (rows, cols, vals, counts)."""
     lib = _lib.load()
     a = _lib.KnnArgs()
@@ -54,9 +55,14 @@ def _host_call(targets, A, B, vecs, scal, k, filt=None, targ=None, threads=0, pa
     vals, counts = np.full(n, np.nan, np.float32), np.full(len(targets), -7, np.int32)
     a.out_rows = _ptr(rows) if with_rows else None
     a.out_cols, a.out_values, a.out_counts = _ptr(cols), _ptr(vals), _ptr(counts)
-    a.threads, a.panel_width = threads, panel_width
-    _lib.check(lib.spy_knn_topk_host(C.byref(a), 0))
-    return rows, cols, vals, counts
+    a.threads, a.panel_width, a.engine = threads, panel_width, engine
+    if devices is None:
+        _lib.check(lib.spy_knn_topk_host(C.byref(a), 0))
+        return rows, cols, vals, counts
+    dev = np.asarray(devices, dtype=np.int32)
+    bounds = np.full(len(dev) + 1, -1, np.int32)
+    _lib.check(lib.spy_knn_topk_multi_host(C.byref(a), _ptr(dev), len(dev), 1, _ptr(bounds)))
+    return rows, cols, vals, counts, bounds
 
 
 def _slab_to_csr(cols, vals, counts, targets, k, shape):
@@ -86,8 +92,8 @@ def _oracle_slab(targets, A, B, vecs, scal, k, filt=None, targ=None):
     return sp.csr_array((vals, (rows, cols)), shape=(A.shape[0], B.shape[1]))
 
 
-@pytest.mark.parametrize("panel_width", [0, 256])
-def test_host_entry_cosine_like(panel_width):
+@pytest.mark.parametrize("engine,panel_width", [(1, 0), (1, 256), (2, 0), (0, 0)], ids=["flat", "flat-panels", "stream", "auto"])
+def test_host_entry_cosine_like(engine, panel_width):
     urm = random_csr(700, 900, 0.04, 3)
     A, B = urm.T.tocsr(), urm
     A.sort_indices(); B.sort_indices()
@@ -97,7 +103,7 @@ def test_host_entry_cosine_like(panel_width):
     scal = dict(SCAL0, l2=1.0, stabilized_shrink=3.0)
     targets = np.arange(0, 900, 2, dtype=np.int32)
     k = 30
-    rows, cols, vals, counts = _host_call(targets, A, B, vecs, scal, k, panel_width=panel_width)
+    rows, cols, vals, counts = _host_call(targets, A, B, vecs, scal, k, panel_width=panel_width, engine=engine)
     got = _slab_to_csr(cols, vals, counts, targets, k, (A.shape[0], B.shape[1]))
     ref = _oracle_slab(targets, A, B, vecs, scal, k)
     assert_topk_parity(ref, got, k=k, rtol=1e-5, what="host ABI cosine-like")
@@ -139,3 +145,77 @@ def test_host_entry_error_convention():
         _host_call(np.arange(5, dtype=np.int32), urm.T.tocsr(), urm, {}, SCAL0, 5, threads=333)
     msg = _lib.load().spy_last_error().decode()
     assert "threads" in msg
+
+
+@pytest.mark.parametrize("engine,panel_width", [(1, 256), (2, 2048)], ids=["flat", "stream"])
+def test_host_entry_sorts_unsorted_b_rows(engine, panel_width):
+    """The reference accepts unsorted rows of B on its unblocked path (s_plus.h:418-438); the panel split needs them
+    ascending, so the host entry sorts its device copy (the caller's arrays are untouched)."""
+    rng = np.random.default_rng(5)
+    urm = random_csr(400, 5000, 0.02, 11)
+    A, B = urm.T.tocsr(), urm.copy()
+    for r in range(B.shape[0]):  # shuffle every row of B in place
+        s, e = B.indptr[r], B.indptr[r + 1]
+        perm = rng.permutation(e - s)
+        B.indices[s:e] = B.indices[s:e][perm]
+        B.data[s:e] = B.data[s:e][perm]
+    B.has_sorted_indices = False
+    before = B.indices.copy()
+    targets = np.arange(0, 5000, 7, dtype=np.int32)
+    k = 20
+    rows, cols, vals, counts = _host_call(targets, A, B, {}, SCAL0, k, panel_width=panel_width, engine=engine)
+    assert np.array_equal(B.indices, before)
+    got = _slab_to_csr(cols, vals, counts, targets, k, (A.shape[0], B.shape[1]))
+    ref = _oracle_slab(targets, A, B, {}, SCAL0, k)
+    assert_topk_parity(ref, got, k=k, rtol=1e-5, what="host ABI, unsorted B")
+
+
+def test_multi_device_host_entry_matches_single_device():
+    """spy_knn_topk_multi_host with a device list (the same GPU three times on a one-GPU box: three host threads, three
+    ranges) assembles the same slab as the single-device call."""
+    urm = random_csr(800, 700, 0.04, 21)
+    A, B = urm.T.tocsr(), urm
+    sqa = np.asarray(A.multiply(A).sum(axis=1)).ravel().astype(np.float32)
+    sqb = np.asarray(B.multiply(B).sum(axis=0)).ravel().astype(np.float32)
+    vecs = dict(Xcosine=np.sqrt(sqa).astype(np.float32), Ycosine=np.sqrt(sqb).astype(np.float32))
+    scal = dict(SCAL0, l2=1.0)
+    targets = np.arange(700, dtype=np.int32)
+    k = 25
+    r1, c1, v1, n1 = _host_call(targets, A, B, vecs, scal, k)
+    n_dev = max(1, _lib.device_count())
+    devices = [i % n_dev for i in range(3)]
+    r3, c3, v3, n3, bounds = _host_call(targets, A, B, vecs, scal, k, devices=devices)
+    assert bounds[0] == 0 and bounds[-1] == len(targets) and np.all(np.diff(bounds) > 0)
+    work = np.diff(A.indptr)[targets] + 1
+    shares = [work[bounds[i]: bounds[i + 1]].sum() / work.sum() for i in range(3)]
+    assert max(shares) < 0.40  # cut by work, not by row count
+    assert np.array_equal(n1, n3) and np.array_equal(r1, r3)
+    ref = _oracle_slab(targets, A, B, vecs, scal, k)
+    assert_topk_parity(ref, _slab_to_csr(c3, v3, n3, targets, k, (A.shape[0], B.shape[1])), k=k, rtol=1e-5, what="multi-device host ABI")
+    with pytest.raises(_lib.SimilaripyB200Error):
+        _host_call(targets, A, B, vecs, scal, k, devices=[0, 99])
+
+
+@pytest.mark.parametrize("val,idx", [(np.float32, np.int32), (np.float64, np.int64), (np.float32, np.int64)])
+def test_host_normalizer_entries(val, idx):
+    """spy_normalize_rows_host / spy_tfidf_host / spy_bm25plus_host with the arrays of a scipy CSR matrix, as the reference's
+    Cython functions receive them (normalization.pyx:97-102, 200-208, 260-271), against the oracle."""
+    lib = _lib.load()
+    m = random_csr(300, 200, 0.06, 31).astype(val)
+    m.indices, m.indptr = m.indices.astype(idx), m.indptr.astype(idx)
+    vd = _lib.F32 if val == np.float32 else _lib.F64
+    xd = _lib.I32 if idx == np.int32 else _lib.I64
+    rtol = 1e-5 if val == np.float32 else 1e-12
+    for code, norm in enumerate(("l1", "l2", "max")):
+        d = m.data.copy()
+        _lib.check(lib.spy_normalize_rows_host(code, m.shape[0], _ptr(d), vd, _ptr(m.indptr), xd, 0))
+        np.testing.assert_allclose(d, oracle.normalize(m, norm=norm).data, rtol=rtol)
+    d = m.data.copy()
+    _lib.check(lib.spy_tfidf_host(m.shape[0], m.shape[1], _ptr(d), vd, _ptr(m.indices), _ptr(m.indptr), xd,
+                                  _lib.TF_MODES["sqrt"], _lib.IDF_MODES["smooth"], float(np.e), 0))
+    np.testing.assert_allclose(d, oracle.tfidf(m).data, rtol=max(rtol, 1e-6))
+    d = m.data.copy()
+    _lib.check(lib.spy_bm25plus_host(m.shape[0], m.shape[1], _ptr(d), vd, _ptr(m.indices), _ptr(m.indptr), xd, 1.2, 0.75, 1.0,
+                                     _lib.TF_MODES["raw"], _lib.IDF_MODES["bm25"], float(np.e), 0))
+    np.testing.assert_allclose(d, oracle.bm25plus(m).data, rtol=max(rtol, 1e-5))
+    assert lib.spy_normalize_rows_host(9, m.shape[0], _ptr(d), vd, _ptr(m.indptr), xd, 0) < 0
