@@ -192,6 +192,17 @@ int spy_knn_topk_dev(const spy_knn_args *args, void *scratch, int64_t scratch_by
  * host arrays of n_targets*k entries. */
 int spy_knn_topk_host(const spy_knn_args *host_args, int device);
 
+/* The same result in the REFERENCE'S OWN ORDER (opt-in, slower): float sums built entry by entry of the target row
+ * (s_plus.h:418-438), candidates enlisted like SparseMatrixMultiplier::add (s_plus.h:112-117), ties at the k-th
+ * value kept like TopK's heap keeps them (s_plus.h:45-59; closed form in csrc/knn_reforder.cu).  Takes plain CSR
+ * operands (no launch plan, no stream layouts).  block_size > 0 and < n_cols: the blocked path (s_plus.h:350-410) --
+ * the caller passes matrix2, the Y vectors and the selector matrices with columns permuted by popularity
+ * (s_plus_utils.pyx:493-618) and out_col_map = the back permutation; ties then compare permuted ids, like the
+ * reference's heap.  out_col_map may be NULL (identity). */
+int64_t spy_knn_reforder_scratch_bytes(const spy_knn_args *args);
+int spy_knn_topk_reforder_dev(const spy_knn_args *args, int32_t block_size, const int32_t *out_col_map, void *scratch,
+                              int64_t scratch_bytes, void *stream);
+
 /* The same call over several GPUs of one box from one process: the target rows are cut into
  * n_devices contiguous ranges of equal work (stored entries of A), every range runs on its device from its own host
  * thread, B is replicated.  The caller's slab is the complete result in target order (assemble is accepted for

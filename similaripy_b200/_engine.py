@@ -113,6 +113,7 @@ class DeviceCSR:
     indices: object
     data: object
     sorted_rows: bool = False
+    scatter_order: bool = False  # rows in the arbitrary arrival order of an unsorted GPU transposition (not the caller's order)
     # Operands prepared once and reused by later calls on the same handle (s_plus.pyx:205-269 redoes all of this on
     # every call): transposes, the row-sorted copy, squared norms / sums, the kernel's stream layouts and split
     # tables.  Anything that overwrites `data` in place must call invalidate().
@@ -212,7 +213,7 @@ def transpose_csr(ctx: Ctx, m: DeviceCSR, sort: bool = True) -> DeviceCSR:
     _lib.check(ctx.lib.spy_csr_transpose_dev(m.n_rows, m.n_cols, _ptr(m.indptr), _ptr(m.indices), _ptr(m.data),
                                              _ptr(t_indptr), _ptr(t_indices), _ptr(t_data), _ptr(cursor), 1 if sort else 0,
                                              ctx.sptr))
-    return DeviceCSR(m.n_cols, m.n_rows, t_indptr, t_indices, t_data, sorted_rows=bool(sort))
+    return DeviceCSR(m.n_cols, m.n_rows, t_indptr, t_indices, t_data, sorted_rows=bool(sort), scatter_order=not sort)
 
 
 def cached_transpose(ctx: Ctx, m: DeviceCSR, sort: bool = True) -> DeviceCSR:
@@ -575,6 +576,10 @@ class KnnJob:
         a.group = int(self.tuning.get("group", 0))
         a.b_nnz = B.nnz
         a.a_nnz = A.nnz
+        if self.tuning.get("tie_mode", "deterministic") == "reference":
+            self._alloc_outputs(a)
+            self.args = a
+            return
         # "engine": that kernel generation or an error; "engine_prefer": that one when it covers the configuration
         eng = self.tuning.get("engine", 0)
         prefer = self.tuning.get("engine_prefer") if not eng else None
@@ -635,6 +640,16 @@ class KnnJob:
             pairs = B.cached("pairs", build_pairs)
             a.b_pairs = _ptr(pairs)
             self.keep.append(pairs)
+        self._alloc_outputs(a)
+        sb = int(lib.spy_knn_scratch_bytes(C.byref(a), ctx.index))
+        if sb < 0:
+            _lib.check(sb)
+        self.scratch = ctx.empty(sb, torch.uint8)
+        self.scratch_bytes = sb
+        self.args = a
+
+    def _alloc_outputs(self, a):
+        ctx, torch = self.ctx, self.ctx.torch
         slab = self.n_targets * self.k
         if self.exchange is not None:  # the kernel writes into this rank's slice of the all-gather buffer
             self.out_cols, self.out_vals, self.out_counts = self.exchange.local()
@@ -644,12 +659,60 @@ class KnnJob:
             self.out_counts = ctx.empty(max(self.n_targets, 1), torch.int32)
         a.out_rows = None
         a.out_cols, a.out_values, a.out_counts = _ptr(self.out_cols), _ptr(self.out_vals), _ptr(self.out_counts)
-        sb = int(lib.spy_knn_scratch_bytes(C.byref(a), ctx.index))
+
+    # ---- the reference's own order (tuning={"tie_mode": "reference"}) --------------------------------------------
+    def run_reference_order(self, block_size):
+        """Same result as run(), computed in the reference's order (csrc/knn_reforder.cu): float sums entry by entry of the
+        target row, ties at the k-th value resolved like its heap -- including the blocked path, where matrix2's columns
+        are permuted by popularity first (s_plus.pyx:218-225, 308-346; s_plus_utils.pyx:493-618) and the heap compares the
+        permuted ids.  Slower by design; for callers that need the reference's index sets on tie-heavy data."""
+        ctx, lib, torch = self.ctx, self.ctx.lib, self.ctx.torch
+        a, n_cols = self.args, self.n_cols
+        A = sorted_rows(ctx, self.A)  # scipy's tocsr of matrix1 yields ascending columns; an unsorted GPU transposition does not
+        B = sorted_rows(ctx, self.B) if self.B.scatter_order else self.B  # otherwise the caller's stored order, like the reference
+        bs = 0 if block_size is None else (262144 if block_size == 0 else int(block_size))  # s_plus.pyx:218-225, s_plus.h:33
+        blocking = bs > 0 and n_cols > bs
+        keep = [A, B]
+        back = None
+        v = dict(self.vectors)
+        f_m, t_m = self.filter_m, self.target_m
+        if blocking:  # _reorder_columns_by_popularity
+            col_nnz = torch.bincount(B.indices.long(), minlength=n_cols)
+            back = torch.sort(col_nnz, descending=True, stable=True).indices.to(torch.int32)
+            if bool((back == torch.arange(n_cols, device=back.device, dtype=torch.int32)).all()):
+                back = None
+            else:
+                fwd = torch.empty(n_cols, dtype=torch.int32, device=back.device)
+                fwd[back.long()] = torch.arange(n_cols, device=back.device, dtype=torch.int32)
+
+                def permuted(indptr, indices, data, n_rows):
+                    m = DeviceCSR(n_rows, n_cols, indptr, fwd[indices.long()].contiguous(),
+                                  data.clone() if data is not None else ctx.zeros(indices.numel(), torch.float32))
+                    _lib.check(lib.spy_csr_sort_rows_dev(n_rows, _ptr(m.indptr), _ptr(m.indices), _ptr(m.data), ctx.sptr))
+                    return m
+                B = permuted(B.indptr, B.indices, B.data, B.n_rows)
+                for name in ("Yt", "Yc", "Yd"):
+                    if name in v:
+                        v[name] = v[name][back.long()].contiguous()
+                if self.filter_mode == MODE_MATRIX:
+                    m = permuted(f_m[0], f_m[1], None, self.n_rows)
+                    f_m = (m.indptr, m.indices)
+                if self.target_mode == MODE_MATRIX:
+                    m = permuted(t_m[0], t_m[1], None, self.n_rows)
+                    t_m = (m.indptr, m.indices)
+                keep += [B, fwd]
+        a.a_indptr, a.a_indices, a.a_data = _ptr(A.indptr), _ptr(A.indices), _ptr(A.data)
+        a.b_indptr, a.b_indices, a.b_data = _ptr(B.indptr), _ptr(B.indices), _ptr(B.data)
+        a.Ytversky, a.Ycosine, a.Ydepop = _ptr(v.get("Yt")), _ptr(v.get("Yc")), _ptr(v.get("Yd"))
+        a.filter_indptr, a.filter_indices = _ptr(f_m[0]), _ptr(f_m[1])
+        a.target_indptr, a.target_indices = _ptr(t_m[0]), _ptr(t_m[1])
+        sb = int(lib.spy_knn_reforder_scratch_bytes(C.byref(a)))
         if sb < 0:
             _lib.check(sb)
-        self.scratch = ctx.empty(sb, torch.uint8)
-        self.scratch_bytes = sb
-        self.args = a
+        scratch = ctx.empty(sb, torch.uint8)
+        _lib.check(lib.spy_knn_topk_reforder_dev(C.byref(a), bs if blocking else 0, _ptr(back), _ptr(scratch), sb, ctx.sptr))
+        ctx.sync()  # the permuted operands and the scratch are released on return
+        del keep, v, f_m, t_m
 
     # ---- the hot kernel ---------------------------------------------------------------------------
     def run(self):
@@ -797,7 +860,10 @@ def s_plus(matrix1, matrix2=None, weight_depop_matrix1="none", weight_depop_matr
                       target_rows, filter_cols, target_cols, verbose, format_output, num_threads, block_size,
                       device, tuning)
     if job.n_targets > 0:
-        job.run()
+        if job.tuning.get("tie_mode", "deterministic") == "reference":
+            job.run_reference_order(block_size)
+        else:
+            job.run()
     if job.exchange is not None:
         job.gather()
     if on_device:

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 LIB = os.path.join(PKG, "libsimilaripy_b200.so")
 SOURCES = ("api.cu", "knn_kernel.cu", "knn_stream.cu", "knn_inst_g4.cu", "knn_inst_g8.cu", "knn_inst_g16.cu", "knn_inst_g32.cu",
-           "csr_ops.cu", "normalize.cu", "host_api.cu")
+           "csr_ops.cu", "normalize.cu", "host_api.cu", "knn_reforder.cu")
 HEADERS = ("common.cuh", "knn_kernel.cuh", "knn_stream_kernel.cuh", "knn_inst.inc", os.path.join("..", "..", "include", "similaripy_b200.h"))
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
