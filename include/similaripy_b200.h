@@ -130,8 +130,8 @@ typedef struct spy_knn_args {
      * alternate; every configuration), SPY_ENGINE_STREAM = knn_stream_kernel (cp.async ring, the panel is
      * snapshotted into tensor memory and drained concurrently; needs the three tables below) */
     int32_t engine;
-    const int32_t *b_chunk_indptr; /* [b_rows + 1] first 16-byte chunk of every row of B in b_chunks          */
-    const void *b_chunks;       /* B as chunks of two (column, value) pairs, rows padded to whole chunks
+    const int32_t *b_chunk_indptr; /* [b_rows * n_panels + 1] first 16-byte chunk of every (row, panel) segment of B  */
+    const void *b_chunks;       /* B as chunks of two (column, value) pairs, segments padded to whole chunks
                                  * (spy_knn_pad_chunks_dev)                                                  */
     const int64_t *toff;        /* [n_targets + 1] exclusive scan of the target rows' lengths               */
     int64_t n_entries;          /* toff[n_targets]: stored entries of A in the target rows                    */
@@ -167,20 +167,24 @@ int spy_knn_build_split_dev(int32_t b_rows, const int32_t *b_indptr, const int32
 int spy_knn_pack_pairs_dev(int64_t nnz, const int32_t *b_indices, const float *b_data, void *pairs_out,
                            void *stream);
 
-/* ---- tables of the stream engine (SPY_ENGINE_STREAM), built once per call on the device ----------------
- * counts[u] = chunks of row u of B = ceil(nnz(B[u,:]) / 2); the caller scans them into chunk_indptr
- * (spy_exclusive_scan_i32_dev) */
-int spy_knn_chunk_counts_dev(int32_t b_rows, const int32_t *b_indptr, int32_t *counts, void *stream);
-/* chunks_out[chunk_indptr[u] + c] = pairs 2c, 2c+1 of row u as (column, value bits, column, value bits); an odd row
- * ends with the filler pair (0xffffffff, 0), which no panel accepts.  chunks_out holds chunk_indptr[b_rows] * 16 bytes. */
+/* ---- tables of the stream engine (SPY_ENGINE_STREAM), built on the device ------------------------------------
+ * Every (row u of B, panel p) segment -- the entries of B[u,:] with columns in panel p -- is stored as whole 16-byte
+ * chunks of two (column, value bits) pairs; inside a segment the pairs are ordered by shared-memory bank of their
+ * accumulator slot (column mod 32), an odd segment ends with the filler pair (0xffffffff, 0).
+ *   counts[u * n_panels + p] = chunks of the segment; the caller scans them into chunk_indptr
+ *   (spy_exclusive_scan_i32_dev, b_rows * n_panels + 1 entries).  b_split may be NULL when n_panels == 1. */
+int spy_knn_chunk_counts_dev(int32_t b_rows, const int32_t *b_indptr, const int32_t *b_split, int32_t split_stride,
+                             int32_t n_panels, int32_t *counts, void *stream);
+/* chunks_out holds chunk_indptr[b_rows * n_panels] * 16 bytes */
 int spy_knn_pad_chunks_dev(int32_t b_rows, const int32_t *b_indptr, const int32_t *b_indices, const float *b_data,
-                           const int32_t *chunk_indptr, void *chunks_out, void *stream);
+                           const int32_t *b_split, int32_t split_stride, int32_t n_panels, const int32_t *chunk_indptr,
+                           void *chunks_out, void *stream);
 /* len[i] = stored entries of target row i; the caller scans them into toff (spy_exclusive_scan_i64_dev) */
 int spy_knn_row_lengths_dev(int32_t n_targets, const int32_t *targets, const int32_t *a_indptr, int32_t *len, void *stream);
 /* aexp[p * n_entries + toff[i] + j] = chunk range of the part of B[u,:] (u = j-th entry of target row i) that falls
  * into panel p.  Replaces the per-(target row, block, B row) std::lower_bound of the blocked path
- * (s_plus.h:381-394) by one coalesced table per call.  Uses targets, a_*, b_indptr, b_chunk_indptr, b_split /
- * split_stride / n_panels (b_split may be NULL when n_panels == 1), toff, n_entries of *args; writes args->aexp. */
+ * (s_plus.h:381-394) by one coalesced table per call.  Uses targets, a_*, b_chunk_indptr, n_panels, toff, n_entries of
+ * *args; writes args->aexp. */
 int spy_knn_build_aexp_dev(const spy_knn_args *args, void *stream);
 
 /* The hot path.  Replaces s_plus::compute_similarities_parallel<int,float>

@@ -36,8 +36,8 @@ struct Lib {
     int (*topk)(const spy_knn_args *, void *, int64_t, void *);
     const char *(*last_error)(void);
     // stream engine tables (absent in round-1 builds)
-    int (*chunk_counts)(int32_t, const int32_t *, int32_t *, void *);
-    int (*pad_chunks)(int32_t, const int32_t *, const int32_t *, const float *, const int32_t *, void *, void *);
+    int (*chunk_counts)(int32_t, const int32_t *, const int32_t *, int32_t, int32_t, int32_t *, void *);
+    int (*pad_chunks)(int32_t, const int32_t *, const int32_t *, const float *, const int32_t *, int32_t, int32_t, const int32_t *, void *, void *);
     int (*row_lengths)(int32_t, const int32_t *, const int32_t *, int32_t *, void *);
     int (*build_aexp)(const spy_knn_args *, void *);
     int64_t (*scan_tmp)(int64_t);
@@ -155,16 +155,17 @@ int main(int argc, char **argv) {
         if (!rc && a.engine == 2) {
             if (!L.chunk_counts || !L.pad_chunks || !L.row_lengths || !L.build_aexp) { printf("%s: no stream engine\n", argv[li]); continue; }
             cudaEvent_t p0, p1; cudaEventCreate(&p0); cudaEventCreate(&p1);
-            const int64_t n_scan = std::max(R, n_t);
-            CK(cudaMalloc(&d_cnt, (size_t)n_scan * 4)); CK(cudaMalloc(&d_cptr, ((size_t)R + 1) * 4));
+            const int64_t n_seg = (int64_t)R * a.n_panels;
+            const int64_t n_scan = std::max<int64_t>(std::max(R, n_t), n_seg);
+            CK(cudaMalloc(&d_cnt, (size_t)n_scan * 4)); CK(cudaMalloc(&d_cptr, ((size_t)n_seg + 1) * 4));
             CK(cudaMalloc(&d_tmp, (size_t)L.scan_tmp(n_scan))); CK(cudaMalloc(&d_toff, ((size_t)n_t + 1) * 8));
             CK(cudaEventRecord(p0));
-            rc = L.chunk_counts(R, a.b_indptr, (int32_t *)d_cnt, nullptr);
-            if (!rc) rc = L.scan32(R, (const int32_t *)d_cnt, (int32_t *)d_cptr, d_tmp, nullptr);
+            rc = L.chunk_counts(R, a.b_indptr, a.b_split, a.split_stride, a.n_panels, (int32_t *)d_cnt, nullptr);
+            if (!rc) rc = L.scan32(n_seg, (const int32_t *)d_cnt, (int32_t *)d_cptr, d_tmp, nullptr);
             int32_t n_chunks = 0;
-            CK(cudaMemcpy(&n_chunks, (int32_t *)d_cptr + R, 4, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(&n_chunks, (int32_t *)d_cptr + n_seg, 4, cudaMemcpyDeviceToHost));
             CK(cudaMalloc(&d_chunks, (size_t)std::max(n_chunks, 1) * 16));
-            if (!rc) rc = L.pad_chunks(R, a.b_indptr, a.b_indices, a.b_data, (const int32_t *)d_cptr, d_chunks, nullptr);
+            if (!rc) rc = L.pad_chunks(R, a.b_indptr, a.b_indices, a.b_data, a.b_split, a.split_stride, a.n_panels, (const int32_t *)d_cptr, d_chunks, nullptr);
             if (!rc) rc = L.row_lengths(n_t, a.targets, a.a_indptr, (int32_t *)d_cnt, nullptr);
             if (!rc) rc = L.scan64(n_t, (const int32_t *)d_cnt, (int64_t *)d_toff, d_tmp, nullptr);
             int64_t n_entries = 0;

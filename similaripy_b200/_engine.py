@@ -8,6 +8,7 @@ There is no CPU fallback: without the CUDA library or without a GPU the calls ra
 from __future__ import annotations
 
 import ctypes as C
+import functools
 import os
 from dataclasses import dataclass, field
 from typing import Optional
@@ -47,6 +48,21 @@ def resolve_device(device=None):
     if isinstance(device, int):
         return torch.device("cuda", device)
     return torch.device(device)
+
+
+def preserve_device(fn):
+    """Public entry points run on the device they were asked for and leave the caller's current CUDA device as it was
+    (the C library launches on the current device, so a call on another device has to switch)."""
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        torch = _torch()
+        prev = torch.cuda.current_device() if torch.cuda.is_available() else None
+        try:
+            return fn(*args, **kwargs)
+        finally:
+            if prev is not None and torch.cuda.current_device() != prev:
+                torch.cuda.set_device(prev)
+    return wrapper
 
 
 def _ptr(t) -> Optional[int]:
@@ -605,16 +621,20 @@ class KnnJob:
             a.b_split = _ptr(split)
             self.keep.append(split)
         if a.engine == _lib.ENGINE_STREAM:
-            def build_chunks():  # B as 16-byte chunks of two (column, value) pairs, every row padded to whole chunks
-                cnt = ctx.empty(max(B.n_rows, 1), torch.int32)[: B.n_rows]
-                _lib.check(lib.spy_knn_chunk_counts_dev(B.n_rows, _ptr(B.indptr), _ptr(cnt), ctx.sptr))
+            n_p, stride = int(a.n_panels), int(a.split_stride)
+            split_ptr = a.b_split
+
+            def build_chunks():  # every (row, panel) segment of B as whole 16-byte chunks of two (column, value) pairs
+                n_seg = B.n_rows * n_p
+                cnt = ctx.empty(max(n_seg, 1), torch.int32)[: n_seg]
+                _lib.check(lib.spy_knn_chunk_counts_dev(B.n_rows, _ptr(B.indptr), split_ptr, stride, n_p, _ptr(cnt), ctx.sptr))
                 chunk_indptr = ctx.scan_i32(cnt)
-                n_chunks = int(chunk_indptr[-1].item()) if B.n_rows > 0 else 0
+                n_chunks = int(chunk_indptr[-1].item()) if n_seg > 0 else 0
                 chunks = ctx.empty(max(n_chunks, 1) * 4, torch.int32)
-                _lib.check(lib.spy_knn_pad_chunks_dev(B.n_rows, _ptr(B.indptr), _ptr(B.indices), _ptr(B.data),
+                _lib.check(lib.spy_knn_pad_chunks_dev(B.n_rows, _ptr(B.indptr), _ptr(B.indices), _ptr(B.data), split_ptr, stride, n_p,
                                                       _ptr(chunk_indptr), _ptr(chunks), ctx.sptr))
                 return chunk_indptr, chunks
-            chunk_indptr, chunks = B.cached("chunks", build_chunks)
+            chunk_indptr, chunks = B.cached(("chunks", int(a.panel_width), n_p), build_chunks)
             a.b_chunk_indptr, a.b_chunks = _ptr(chunk_indptr), _ptr(chunks)
 
             def build_tables():  # chunk range of every (entry of a target row, panel)
@@ -843,6 +863,7 @@ def prepare_job(matrix1, matrix2=None, weight_depop_matrix1="none", weight_depop
     return job
 
 
+@preserve_device
 def s_plus(matrix1, matrix2=None, weight_depop_matrix1="none", weight_depop_matrix2="none",
            p1=0.0, p2=0.0, a1=1.0, l1=0.0, l2=0.0, l3=0.0, t1=1.0, t2=1.0, c1=0.5, c2=0.5, k=100,
            stabilized_shrink=0.0, bayesian_shrink=0.0, additive_shrink=0.0, threshold=0.0, binary=False,
@@ -871,6 +892,7 @@ def s_plus(matrix1, matrix2=None, weight_depop_matrix1="none", weight_depop_matr
     return job.to_host(job.assemble_device(format_output))
 
 
+@preserve_device
 def to_device(matrix, device=None) -> DeviceMatrix:
     """Upload a scipy sparse matrix once (zero-free, float32 values, int32 indices) and return a handle the
     similarity functions accept in place of ``matrix1`` / ``matrix2``."""
@@ -884,6 +906,7 @@ def to_device(matrix, device=None) -> DeviceMatrix:
     return DeviceMatrix(stored, transposed)
 
 
+@preserve_device
 def axis_sum(m: DeviceMatrix, axis: int):
     """``matrix.sum(axis)`` of a DeviceMatrix as a float32 device tensor (similarity.py:479)."""
     ctx = Ctx(m.device)
@@ -900,6 +923,7 @@ def axis_sum(m: DeviceMatrix, axis: int):
     return out
 
 
+@preserve_device
 def pow_values_(m: DeviceMatrix, p: float) -> DeviceMatrix:
     """``m.data = m.data ** p`` in place on the device (similarity.py:411-415, 480-483)."""
     ctx = Ctx(m.device)

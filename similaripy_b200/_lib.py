@@ -53,8 +53,8 @@ SIGNATURES = {
     "spy_knn_scratch_bytes": (_i64, [C.POINTER(KnnArgs), C.c_int]),
     "spy_knn_build_split_dev": (C.c_int, [_i32, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),
     "spy_knn_row_work_dev": (C.c_int, [_i32, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "spy_knn_chunk_counts_dev": (C.c_int, [_i32, _vp, _vp, _vp]),
-    "spy_knn_pad_chunks_dev": (C.c_int, [_i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "spy_knn_chunk_counts_dev": (C.c_int, [_i32, _vp, _vp, _i32, _i32, _vp, _vp]),
+    "spy_knn_pad_chunks_dev": (C.c_int, [_i32, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "spy_knn_row_lengths_dev": (C.c_int, [_i32, _vp, _vp, _vp, _vp]),
     "spy_knn_build_aexp_dev": (C.c_int, [C.POINTER(KnnArgs), _vp]),
     "spy_knn_topk_dev": (C.c_int, [C.POINTER(KnnArgs), _vp, _i64, _vp]),

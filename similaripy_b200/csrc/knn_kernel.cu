@@ -463,16 +463,18 @@ int spy_knn_topk_host(const spy_knn_args *host_args, int device) {
         // the stream engine's tables: B as padded 16-byte chunks, the chunk range of every (entry, panel)
         void *d_cnt = nullptr, *d_cptr = nullptr, *d_tmp = nullptr, *d_chunks = nullptr, *d_len = nullptr, *d_toff = nullptr, *d_aexp = nullptr;
         const int64_t n_scan = std::max<int64_t>(std::max(a.b_rows, a.n_targets), 1);
-        if (!dev_alloc(&d_cnt, (size_t)n_scan * 4) || !dev_alloc(&d_cptr, ((size_t)a.b_rows + 1) * 4) ||
-            !dev_alloc(&d_tmp, (size_t)spy_scan_tmp_bytes(n_scan)) || !dev_alloc(&d_toff, ((size_t)a.n_targets + 1) * 8)) { cleanup(); return SPY_ERR_NOMEM; }
+        const int64_t n_seg = (int64_t)a.b_rows * a.n_panels;
+        if (!dev_alloc(&d_cnt, (size_t)std::max(n_scan, n_seg) * 4) || !dev_alloc(&d_cptr, ((size_t)n_seg + 1) * 4) ||
+            !dev_alloc(&d_tmp, (size_t)spy_scan_tmp_bytes(std::max(n_scan, n_seg))) || !dev_alloc(&d_toff, ((size_t)a.n_targets + 1) * 8)) { cleanup(); return SPY_ERR_NOMEM; }
         d_len = d_cnt;
-        rc = spy_knn_chunk_counts_dev(a.b_rows, a.b_indptr, (int32_t *)d_cnt, nullptr);
-        if (rc == SPY_OK) rc = spy_exclusive_scan_i32_dev(a.b_rows, (const int32_t *)d_cnt, (int32_t *)d_cptr, d_tmp, nullptr);
+        rc = spy_knn_chunk_counts_dev(a.b_rows, a.b_indptr, a.b_split, a.split_stride, a.n_panels, (int32_t *)d_cnt, nullptr);
+        if (rc == SPY_OK) rc = spy_exclusive_scan_i32_dev(n_seg, (const int32_t *)d_cnt, (int32_t *)d_cptr, d_tmp, nullptr);
         int32_t n_chunks = 0;
-        if (rc == SPY_OK && cudaMemcpy(&n_chunks, (int32_t *)d_cptr + a.b_rows, 4, cudaMemcpyDeviceToHost) != cudaSuccess) rc = SPY_ERR_CUDA;
+        if (rc == SPY_OK && cudaMemcpy(&n_chunks, (int32_t *)d_cptr + n_seg, 4, cudaMemcpyDeviceToHost) != cudaSuccess) rc = SPY_ERR_CUDA;
         if (rc != SPY_OK) { cleanup(); return rc; }
         if (!dev_alloc(&d_chunks, ((size_t)std::max(n_chunks, 1)) * 16)) { cleanup(); return SPY_ERR_NOMEM; }
-        rc = spy_knn_pad_chunks_dev(a.b_rows, a.b_indptr, a.b_indices, a.b_data, (const int32_t *)d_cptr, d_chunks, nullptr);
+        rc = spy_knn_pad_chunks_dev(a.b_rows, a.b_indptr, a.b_indices, a.b_data, a.b_split, a.split_stride, a.n_panels,
+                                    (const int32_t *)d_cptr, d_chunks, nullptr);
         if (rc == SPY_OK) rc = spy_knn_row_lengths_dev(a.n_targets, a.targets, a.a_indptr, (int32_t *)d_len, nullptr);
         if (rc == SPY_OK) rc = spy_exclusive_scan_i64_dev(a.n_targets, (const int32_t *)d_len, (int64_t *)d_toff, d_tmp, nullptr);
         int64_t n_entries = 0;

@@ -5,31 +5,60 @@
 
 namespace spy {
 
-// counts[u] = ceil(nnz(B[u,:]) / 2)
-__global__ void chunk_counts_kernel(int b_rows, const int *__restrict__ b_indptr, int *__restrict__ counts) {
-    const int u = blockIdx.x * blockDim.x + threadIdx.x;
-    if (u < b_rows) counts[u] = (b_indptr[u + 1] - b_indptr[u] + 1) >> 1;
+// Stream layout of B: every (row u, panel p) SEGMENT -- the entries of B[u,:] whose columns fall into panel p -- is stored as
+// whole 16-byte chunks of two (column, value) pairs, at chunks [seg[u * P + p], seg[u * P + p + 1]).
+//   counts[u * P + p] = ceil(len(u, p) / 2)
+__global__ void chunk_counts_kernel(int b_rows, const int *__restrict__ b_indptr, const int *__restrict__ split, int split_stride,
+                                    int n_panels, int *__restrict__ counts) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)b_rows * n_panels) return;
+    const int u = (int)(i / n_panels), pn = (int)(i % n_panels);
+    int s, e;
+    if (n_panels == 1) { s = b_indptr[u]; e = b_indptr[u + 1]; }
+    else { s = split[(size_t)u * split_stride + pn]; e = split[(size_t)u * split_stride + pn + 1]; }
+    counts[i] = (e - s + 1) >> 1;
 }
 
-// one warp per row of B: chunk c of the row = its pairs 2c and 2c + 1 (filler (0xffffffff, 0) after an odd row)
+// One warp per row of B.  Inside a segment the pairs are ordered by SHARED-MEMORY BANK of their accumulator slot (column
+// mod 32): the expansion adds pair 0 of 32 consecutive chunks with one instruction and pair 1 with the next, i.e. the
+// even and the odd positions of 64 consecutive pairs -- in bank order each of the two sets touches a bank at most
+// ceil(m / 2) times when the segment holds m columns of that bank, instead of the ~3.5-way conflicts of 32 random banks
+// (the kernel is bound by shared-memory wavefronts: profiles/r02/knn_stream_v1_ncu_summary.txt).  Order inside a segment is
+// free: a segment is a set of (column, value) to be added.  Groups of 64 pairs are ordered independently; an odd segment
+// ends with the filler pair (0xffffffff, 0), which no panel accepts.
 __global__ void pad_chunks_kernel(int b_rows, const int *__restrict__ b_indptr, const int *__restrict__ b_indices,
-                                  const float *__restrict__ b_data, const int *__restrict__ chunk_indptr,
-                                  uint4 *__restrict__ chunks) {
+                                  const float *__restrict__ b_data, const int *__restrict__ split, int split_stride,
+                                  int n_panels, const int *__restrict__ seg, uint2 *__restrict__ pairs_out) {
     const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
     const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
     for (long long u = warp0; u < b_rows; u += n_warps) {
-        const int s = b_indptr[u], e = b_indptr[u + 1], c0 = chunk_indptr[u];
-        const int n = (e - s + 1) >> 1;
-        for (int c = lane; c < n; c += 32) {
-            const int q = s + 2 * c;
-            uint4 v;
-            v.x = (unsigned)b_indices[q];
-            v.y = __float_as_uint(b_data[q]);
-            v.z = 0xffffffffu;
-            v.w = 0u;
-            if (q + 1 < e) { v.z = (unsigned)b_indices[q + 1]; v.w = __float_as_uint(b_data[q + 1]); }
-            chunks[c0 + c] = v;
+        for (int pn = 0; pn < n_panels; pn++) {
+            int s, e;
+            if (n_panels == 1) { s = b_indptr[u]; e = b_indptr[u + 1]; }
+            else { s = split[(size_t)u * split_stride + pn]; e = split[(size_t)u * split_stride + pn + 1]; }
+            uint2 *out = pairs_out + 2 * (size_t)seg[u * n_panels + pn];
+            for (int g0 = s; g0 < e; g0 += 64) {  // groups of 64 pairs: two per lane
+                const int q0 = g0 + lane, q1 = g0 + 32 + lane;
+                const bool v0 = q0 < e, v1 = q1 < e;
+                uint2 p0 = make_uint2(0xffffffffu, 0u), p1 = p0;
+                if (v0) p0 = make_uint2((unsigned)b_indices[q0], __float_as_uint(b_data[q0]));
+                if (v1) p1 = make_uint2((unsigned)b_indices[q1], __float_as_uint(b_data[q1]));
+                const int k0 = v0 ? (int)(p0.x & 31u) : 32, k1 = v1 ? (int)(p1.x & 31u) : 32;
+                int pos0 = 0, pos1 = 0;  // counting sort by bank: pairs of smaller banks first, then by position
+                for (int b = 0; b < 32; b++) {
+                    const unsigned m0 = __ballot_sync(0xffffffffu, k0 == b), m1 = __ballot_sync(0xffffffffu, k1 == b);
+                    const int c = __popc(m0) + __popc(m1);
+                    if (b < k0) pos0 += c;
+                    if (b < k1) pos1 += c;
+                    if (b == k0) pos0 += __popc(m0 & lt);
+                    if (b == k1) pos1 += __popc(m0) + __popc(m1 & lt);
+                }
+                if (v0) out[(g0 - s) + pos0] = p0;
+                if (v1) out[(g0 - s) + pos1] = p1;
+            }
+            if (((e - s) & 1) && lane == 0) out[e - s] = make_uint2(0xffffffffu, 0u);
         }
     }
 }
@@ -46,9 +75,8 @@ __global__ void row_lengths_kernel(int n_targets, const int *__restrict__ target
 // one warp per target row: lane j of a step owns one entry (u = its column) and writes the chunk range of B[u,:]
 // inside every panel -- for a fixed panel the 32 lanes write 256 consecutive bytes
 __global__ void build_aexp_kernel(int n_targets, const int *__restrict__ targets, const int *__restrict__ a_indptr,
-                                  const int *__restrict__ a_indices, const int *__restrict__ b_indptr,
-                                  const int *__restrict__ chunk_indptr, const int *__restrict__ split, int split_stride,
-                                  int n_panels, const long long *__restrict__ toff, long long E, uint2 *__restrict__ aexp) {
+                                  const int *__restrict__ a_indices, const int *__restrict__ seg, int n_panels,
+                                  const long long *__restrict__ toff, long long E, uint2 *__restrict__ aexp) {
     const int lane = threadIdx.x & 31;
     const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -57,21 +85,12 @@ __global__ void build_aexp_kernel(int n_targets, const int *__restrict__ targets
         const int a0 = a_indptr[t], len = a_indptr[t + 1] - a0;
         const long long tq0 = toff[i];
         for (int j = lane; j < len; j += 32) {
-            const int u = a_indices[a0 + j];
-            const int bp0 = b_indptr[u], c0 = chunk_indptr[u];
-            if (n_panels == 1) {
-                const int e = b_indptr[u + 1];
-                aexp[tq0 + j] = make_uint2((unsigned)c0, (unsigned)(c0 + ((e - bp0 + 1) >> 1)));
-            } else {
-                const int *sp = split + (size_t)u * split_stride;
-                int s = sp[0];
-                for (int p = 0; p < n_panels; p++) {
-                    const int e = sp[p + 1];
-                    const unsigned cb = (unsigned)(c0 + ((s - bp0) >> 1));
-                    const unsigned ce = e > s ? (unsigned)(c0 + ((e - bp0 + 1) >> 1)) : cb;
-                    aexp[(long long)p * E + tq0 + j] = make_uint2(cb, ce);
-                    s = e;
-                }
+            const int *sp = seg + (size_t)a_indices[a0 + j] * n_panels;
+            int s = sp[0];
+            for (int p = 0; p < n_panels; p++) {
+                const int e = sp[p + 1];
+                aexp[(long long)p * E + tq0 + j] = make_uint2((unsigned)s, (unsigned)e);
+                s = e;
             }
         }
     }
@@ -181,21 +200,27 @@ using namespace spy;
 
 extern "C" {
 
-int spy_knn_chunk_counts_dev(int32_t b_rows, const int32_t *b_indptr, int32_t *counts, void *stream) {
+int spy_knn_chunk_counts_dev(int32_t b_rows, const int32_t *b_indptr, const int32_t *b_split, int32_t split_stride,
+                             int32_t n_panels, int32_t *counts, void *stream) {
     if (b_rows <= 0) return SPY_OK;
-    SPY_REQUIRE(b_indptr && counts, "chunk_counts: NULL pointer");
-    chunk_counts_kernel<<<(b_rows + 255) / 256, 256, 0, as_stream(stream)>>>(b_rows, b_indptr, counts);
+    SPY_REQUIRE(b_indptr && counts && n_panels >= 1, "chunk_counts: bad arguments");
+    SPY_REQUIRE(n_panels == 1 || (b_split && split_stride >= n_panels + 1), "chunk_counts: n_panels > 1 needs b_split");
+    const long long total = (long long)b_rows * n_panels;
+    chunk_counts_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(b_rows, b_indptr, b_split, split_stride,
+                                                                                       n_panels, counts);
     SPY_LAUNCH_OK();
     return SPY_OK;
 }
 
 int spy_knn_pad_chunks_dev(int32_t b_rows, const int32_t *b_indptr, const int32_t *b_indices, const float *b_data,
-                           const int32_t *chunk_indptr, void *chunks_out, void *stream) {
+                           const int32_t *b_split, int32_t split_stride, int32_t n_panels, const int32_t *chunk_indptr,
+                           void *chunks_out, void *stream) {
     if (b_rows <= 0) return SPY_OK;
-    SPY_REQUIRE(b_indptr && chunk_indptr && chunks_out, "pad_chunks: NULL pointer");
+    SPY_REQUIRE(b_indptr && chunk_indptr && chunks_out && n_panels >= 1, "pad_chunks: bad arguments");
+    SPY_REQUIRE(n_panels == 1 || (b_split && split_stride >= n_panels + 1), "pad_chunks: n_panels > 1 needs b_split");
     const long long warps = std::min<long long>(b_rows, (long long)kB200SmCount * 64);
     pad_chunks_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, as_stream(stream)>>>(
-        b_rows, b_indptr, b_indices, b_data, chunk_indptr, reinterpret_cast<uint4 *>(chunks_out));
+        b_rows, b_indptr, b_indices, b_data, b_split, split_stride, n_panels, chunk_indptr, reinterpret_cast<uint2 *>(chunks_out));
     SPY_LAUNCH_OK();
     return SPY_OK;
 }
@@ -213,14 +238,11 @@ int spy_knn_build_aexp_dev(const spy_knn_args *args, void *stream) {
     const spy_knn_args &a = *args;
     if (a.n_targets <= 0 || a.n_entries <= 0) return SPY_OK;
     SPY_REQUIRE(a.n_panels >= 1, "build_aexp: launch plan missing (spy_knn_plan)");
-    SPY_REQUIRE(a.targets && a.a_indptr && a.a_indices && a.b_indptr && a.b_chunk_indptr && a.toff && a.aexp,
-                "build_aexp: NULL pointer");
-    SPY_REQUIRE(a.n_panels == 1 || (a.b_split && a.split_stride >= a.n_panels + 1), "build_aexp: n_panels > 1 needs b_split");
+    SPY_REQUIRE(a.targets && a.a_indptr && a.a_indices && a.b_chunk_indptr && a.toff && a.aexp, "build_aexp: NULL pointer");
     const long long warps = std::min<long long>(a.n_targets, (long long)kB200SmCount * 64);
     build_aexp_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, as_stream(stream)>>>(
-        a.n_targets, a.targets, a.a_indptr, a.a_indices, a.b_indptr, a.b_chunk_indptr, a.b_split, a.split_stride, a.n_panels,
-        reinterpret_cast<const long long *>(a.toff), a.n_entries,
-        reinterpret_cast<uint2 *>(const_cast<void *>(a.aexp)));
+        a.n_targets, a.targets, a.a_indptr, a.a_indices, a.b_chunk_indptr, a.n_panels,
+        reinterpret_cast<const long long *>(a.toff), a.n_entries, reinterpret_cast<uint2 *>(const_cast<void *>(a.aexp)));
     SPY_LAUNCH_OK();
     return SPY_OK;
 }

@@ -12,7 +12,7 @@ import numpy as np
 import scipy.sparse as sps
 
 from . import _lib
-from ._engine import Ctx, DeviceCSR, DeviceMatrix, _ptr, transpose_csr
+from ._engine import Ctx, DeviceCSR, DeviceMatrix, _ptr, preserve_device, transpose_csr
 
 _NORMALIZATIONS = ("l1", "l2", "max")
 _TF_MODES = ("binary", "raw", "sqrt", "freq", "log")
@@ -118,6 +118,7 @@ def _device_weighting(X: DeviceMatrix, axis, inplace, bm25_args, tf_mode, idf_mo
     return DeviceMatrix(s, flag)
 
 
+@preserve_device
 def normalize(X, norm: str = "l2", axis: int = 1, inplace: bool = False, *, device=None):
     """Row (axis=1) or column (axis=0) l1 / l2 / max normalisation (normalization.py:91-113)."""
     if norm not in _NORMALIZATIONS:
@@ -157,18 +158,21 @@ def _weighting(X, axis, inplace, device, bm25_args, tf_mode, idf_mode, logbase):
     return _finalize_csr(X, axis)
 
 
+@preserve_device
 def bm25(X, axis: int = 1, k1: float = 1.2, b: float = 0.75, logbase: float = e, tf_mode: str = "raw",
          idf_mode: str = "bm25", inplace: bool = False, *, device=None):
     """BM25 weighting (normalization.py:116-149): BM25+ with delta = 0."""
     return _weighting(X, axis, inplace, device, (k1, b, 0.0), tf_mode, idf_mode, logbase)
 
 
+@preserve_device
 def bm25plus(X, axis: int = 1, k1: float = 1.2, b: float = 0.75, delta: float = 1.0, logbase: float = e,
              tf_mode: str = "raw", idf_mode: str = "bm25", inplace: bool = False, *, device=None):
     """BM25+ weighting (normalization.py:152-187)."""
     return _weighting(X, axis, inplace, device, (k1, b, delta), tf_mode, idf_mode, logbase)
 
 
+@preserve_device
 def tfidf(X, axis: int = 1, logbase: float = e, tf_mode: str = "sqrt", idf_mode: str = "smooth",
           inplace: bool = False, *, device=None):
     """TF-IDF weighting (normalization.py:190-218)."""
