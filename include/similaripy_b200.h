@@ -297,6 +297,11 @@ int spy_bm25plus_dev(int64_t n_rows, int64_t n_cols, void *data, int val_dtype, 
                      const void *indptr, int idx_dtype, double k1, double b, double delta,
                      int tf_mode, int idf_mode, double logbase, void *scratch, void *stream);
 
+/* Host -> device copy of PAGEABLE memory (what a scipy matrix normally lives in) through two pinned 16 MB staging buffers:
+ * several host threads fill one buffer while the DMA of the other runs on `stream`.  Returns once src_host has been read
+ * (the DMA of the last chunks may still be in flight on the stream). */
+int spy_h2d_staged(void *dst_dev, const void *src_host, int64_t bytes, int device, void *stream);
+
 /* The same three with HOST pointers: exactly the arguments of the reference's Cython functions
  * inplace_normalize_csr_{l1,l2,max} / _tfidf / _bm25plus (normalization.pyx:97-102, 200-208, 260-271) -- the data,
  * indices and indptr arrays of a scipy CSR matrix; `data` is overwritten in place. */

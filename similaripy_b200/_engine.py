@@ -22,6 +22,9 @@ from . import sharded as _sharded
 # Reuse prepared operands across calls on the same DeviceMatrix (SIMILARIPY_B200_CACHE=0 switches it off)
 CACHE_OPERANDS = os.environ.get("SIMILARIPY_B200_CACHE", "1") != "0"
 
+# Pageable host arrays at least this large are uploaded through spy_h2d_staged (0 disables: torch's own staging)
+STAGED_H2D_MIN_BYTES = int(os.environ.get("SIMILARIPY_B200_STAGED_H2D", str(8 << 20))) or (1 << 62)
+
 # Defaults merged under every call's `tuning` (tests switch kernel generations with it): e.g. {"engine_prefer": "stream"}
 DEFAULT_TUNING: dict = {}
 
@@ -93,8 +96,14 @@ class Ctx:
         arr = np.ascontiguousarray(arr)
         if not arr.flags.writeable:
             arr = arr.copy()
-        # pinned host memory (is_pinned) makes this a true async DMA; pageable memory is staged by torch
-        return self.torch.from_numpy(arr).to(self.device, non_blocking=True)
+        # pinned host memory (is_pinned) makes this a true async DMA; large pageable arrays -- what a scipy matrix normally
+        # lives in -- go through the library's two pinned staging buffers filled by several host threads
+        t = self.torch.from_numpy(arr)
+        if arr.nbytes >= STAGED_H2D_MIN_BYTES and not t.is_pinned():
+            out = self.torch.empty(t.shape, dtype=t.dtype, device=self.device)
+            _lib.check(self.lib.spy_h2d_staged(out.data_ptr(), arr.ctypes.data, arr.nbytes, self.index, self.sptr))
+            return out
+        return t.to(self.device, non_blocking=True)
 
     def d2h(self, t) -> np.ndarray:
         host = self.torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
@@ -273,7 +282,7 @@ def filter_csr(ctx: Ctx, m: DeviceCSR, col_mask=None, drop_zeros=False, values=N
     _lib.check(ctx.lib.spy_csr_filter_compact_dev(m.n_rows, _ptr(m.indptr), _ptr(m.indices), _ptr(data),
                                                   _ptr(col_mask), 1 if drop_zeros else 0, _ptr(new_indptr),
                                                   _ptr(new_indices), _ptr(new_data), ctx.sptr))
-    return DeviceCSR(m.n_rows, m.n_cols, new_indptr, new_indices, new_data, sorted_rows=m.sorted_rows)
+    return DeviceCSR(m.n_rows, m.n_cols, new_indptr, new_indices, new_data, sorted_rows=m.sorted_rows, scatter_order=m.scatter_order)
 
 
 def upload_stored(ctx: Ctx, matrix):
@@ -309,7 +318,7 @@ def binarize(ctx: Ctx, m: DeviceCSR) -> DeviceCSR:
     """binary=True: every stored value becomes 1.0 (s_plus_utils.pyx:301-304)."""
     ones = ctx.empty(m.nnz, ctx.torch.float32)
     _lib.check(ctx.lib.spy_cast_values_dev(m.nnz, _ptr(ones), _lib.F32, 1, _ptr(ones), ctx.sptr))
-    return DeviceCSR(m.n_rows, m.n_cols, m.indptr, m.indices, ones, sorted_rows=m.sorted_rows)
+    return DeviceCSR(m.n_rows, m.n_cols, m.indptr, m.indices, ones, sorted_rows=m.sorted_rows, scatter_order=m.scatter_order)
 
 
 def upload_pair(ctx: Ctx, matrix1, matrix2):

@@ -62,6 +62,7 @@ SIGNATURES = {
     "spy_knn_reforder_scratch_bytes": (_i64, [C.POINTER(KnnArgs)]),
     "spy_knn_topk_reforder_dev": (C.c_int, [C.POINTER(KnnArgs), _i32, _vp, _vp, _i64, _vp]),
     "spy_knn_topk_multi_host": (C.c_int, [C.POINTER(KnnArgs), _vp, _i32, _i32, _vp]),
+    "spy_h2d_staged": (C.c_int, [_vp, _vp, _i64, C.c_int, _vp]),
     "spy_normalize_rows_host": (C.c_int, [C.c_int, _i64, _vp, C.c_int, _vp, C.c_int, C.c_int]),
     "spy_tfidf_host": (C.c_int, [_i64, _i64, _vp, C.c_int, _vp, _vp, C.c_int, C.c_int, C.c_int, _f64, C.c_int]),
     "spy_bm25plus_host": (C.c_int, [_i64, _i64, _vp, C.c_int, _vp, _vp, C.c_int, _f64, _f64, _f64, C.c_int, C.c_int, _f64, C.c_int]),

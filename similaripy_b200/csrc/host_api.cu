@@ -3,6 +3,7 @@
 // (normalization.pyx:97-102, 200-208, 260-271: shape, data, indices, indptr of a scipy CSR matrix).
 #include "common.cuh"
 #include <algorithm>
+#include <cstring>
 #include <string>
 #include <thread>
 #include <vector>
@@ -10,6 +11,49 @@
 using namespace spy;
 
 namespace {
+
+// Pageable host memory -> device through two pinned staging buffers: the copy of chunk i + 1 into pinned memory (several
+// host threads) overlaps the DMA of chunk i.  cudaMemcpyAsync from pageable memory stages too, but single-threaded.
+struct Staging {
+    static constexpr size_t kChunk = 16u << 20;
+    void *pinned[2] = {nullptr, nullptr};
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    int device = -1;
+    bool ensure(int dev) {
+        if (pinned[0] && device == dev) return true;
+        release();
+        for (int b = 0; b < 2; b++) {
+            if (cudaHostAlloc(&pinned[b], kChunk, cudaHostAllocDefault) != cudaSuccess) { release(); return false; }
+            if (cudaEventCreateWithFlags(&done[b], cudaEventDisableTiming) != cudaSuccess) { release(); return false; }
+        }
+        device = dev;
+        return true;
+    }
+    void release() {
+        for (int b = 0; b < 2; b++) {
+            if (pinned[b]) cudaFreeHost(pinned[b]);
+            if (done[b]) cudaEventDestroy(done[b]);
+            pinned[b] = nullptr; done[b] = nullptr;
+        }
+        device = -1;
+        cudaGetLastError();
+    }
+    ~Staging() { release(); }
+};
+thread_local Staging g_staging;
+
+void parallel_memcpy(void *dst, const void *src, size_t bytes, int n_threads) {
+    if (n_threads <= 1 || bytes < (4u << 20)) { memcpy(dst, src, bytes); return; }
+    std::vector<std::thread> workers;
+    const size_t part = (bytes / n_threads + 4095) & ~(size_t)4095;
+    for (int t = 1; t < n_threads; t++) {
+        const size_t off = part * t;
+        if (off >= bytes) break;
+        workers.emplace_back([=]() { memcpy((char *)dst + off, (const char *)src + off, std::min(part, bytes - off)); });
+    }
+    memcpy(dst, src, std::min(part, bytes));
+    for (auto &w : workers) w.join();
+}
 
 struct DevBuf {  // device copy of a host array, freed on scope exit
     void *p = nullptr;
@@ -60,6 +104,27 @@ int with_device_csr(int64_t n_rows, void *data, int val_dtype, const void *indic
 }  // namespace
 
 extern "C" {
+
+int spy_h2d_staged(void *dst_dev, const void *src_host, int64_t bytes, int device, void *stream) {
+    if (bytes <= 0) return SPY_OK;
+    SPY_REQUIRE(dst_dev && src_host, "h2d_staged: NULL pointer");
+    SPY_CUDA_OK(cudaSetDevice(device));
+    cudaStream_t st = as_stream(stream);
+    if (!g_staging.ensure(device)) {  // no pinned memory to be had: let the driver stage
+        SPY_CUDA_OK(cudaMemcpyAsync(dst_dev, src_host, (size_t)bytes, cudaMemcpyHostToDevice, st));
+        return SPY_OK;
+    }
+    const int n_threads = (int)std::max(1u, std::min(4u, std::thread::hardware_concurrency() / 2));
+    int b = 0;
+    for (size_t off = 0; off < (size_t)bytes; off += Staging::kChunk, b ^= 1) {
+        const size_t n = std::min(Staging::kChunk, (size_t)bytes - off);
+        SPY_CUDA_OK(cudaEventSynchronize(g_staging.done[b]));  // the buffer's previous DMA has finished (no-op the first time)
+        parallel_memcpy(g_staging.pinned[b], (const char *)src_host + off, n, n_threads);
+        SPY_CUDA_OK(cudaMemcpyAsync((char *)dst_dev + off, g_staging.pinned[b], n, cudaMemcpyHostToDevice, st));
+        SPY_CUDA_OK(cudaEventRecord(g_staging.done[b], st));
+    }
+    return SPY_OK;
+}
 
 int spy_normalize_rows_host(int norm, int64_t n_rows, void *data, int val_dtype, const void *indptr, int idx_dtype, int device) {
     SPY_REQUIRE(norm >= 0 && norm <= 2, "norm must be 0 (l1), 1 (l2) or 2 (max)");

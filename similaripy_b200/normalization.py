@@ -94,7 +94,7 @@ def _device_rows(X: DeviceMatrix, axis: int, inplace: bool):
     if X.transposed != want_transposed:  # stored orientation is the other one: transpose on the device (a copy)
         s = transpose_csr(ctx, s)
     elif not inplace:
-        s = DeviceCSR(s.n_rows, s.n_cols, s.indptr, s.indices, s.data.clone(), sorted_rows=s.sorted_rows)
+        s = DeviceCSR(s.n_rows, s.n_cols, s.indptr, s.indices, s.data.clone(), sorted_rows=s.sorted_rows, scatter_order=s.scatter_order)
     else:
         s.invalidate()  # values are about to be overwritten in place: prepared operands cached on the handle are stale
     return ctx, s, want_transposed
