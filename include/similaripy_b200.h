@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SPY_ABI_VERSION 5
+#define SPY_ABI_VERSION 6
 
 typedef enum {
     SPY_OK = 0,
@@ -169,16 +169,18 @@ int spy_knn_pack_pairs_dev(int64_t nnz, const int32_t *b_indices, const float *b
 
 /* ---- tables of the stream engine (SPY_ENGINE_STREAM), built on the device ------------------------------------
  * Every (row u of B, panel p) segment -- the entries of B[u,:] with columns in panel p -- is stored as whole 16-byte
- * chunks of two (column, value bits) pairs; inside a segment the pairs are ordered by shared-memory bank of their
- * accumulator slot (column mod 32), an odd segment ends with the filler pair (0xffffffff, 0).
+ * chunks of two (byte offset of the column's accumulator slot inside panel p = 4 * (column - p * panel_width), value
+ * bits) pairs; inside a segment the pairs are ordered by shared-memory bank of their slot (column mod 32), an odd
+ * segment ends with the filler pair (4 * panel_width, 0) -- the spare slot behind the panel.
  *   counts[u * n_panels + p] = chunks of the segment; the caller scans them into chunk_indptr
  *   (spy_exclusive_scan_i32_dev, b_rows * n_panels + 1 entries).  b_split may be NULL when n_panels == 1. */
 int spy_knn_chunk_counts_dev(int32_t b_rows, const int32_t *b_indptr, const int32_t *b_split, int32_t split_stride,
                              int32_t n_panels, int32_t *counts, void *stream);
-/* chunks_out holds chunk_indptr[b_rows * n_panels] * 16 bytes */
+/* chunks_out holds chunk_indptr[b_rows * n_panels] * 16 bytes; panel_width = the plan's (the pairs are stored relative to
+ * their panel, see above) */
 int spy_knn_pad_chunks_dev(int32_t b_rows, const int32_t *b_indptr, const int32_t *b_indices, const float *b_data,
                            const int32_t *b_split, int32_t split_stride, int32_t n_panels, const int32_t *chunk_indptr,
-                           void *chunks_out, void *stream);
+                           void *chunks_out, void *stream, int32_t panel_width);
 /* len[i] = stored entries of target row i; the caller scans them into toff (spy_exclusive_scan_i64_dev) */
 int spy_knn_row_lengths_dev(int32_t n_targets, const int32_t *targets, const int32_t *a_indptr, int32_t *len, void *stream);
 /* aexp[p * n_entries + toff[i] + j] = chunk range of the part of B[u,:] (u = j-th entry of target row i) that falls

@@ -37,7 +37,7 @@ struct Lib {
     const char *(*last_error)(void);
     // stream engine tables (absent in round-1 builds)
     int (*chunk_counts)(int32_t, const int32_t *, const int32_t *, int32_t, int32_t, int32_t *, void *);
-    int (*pad_chunks)(int32_t, const int32_t *, const int32_t *, const float *, const int32_t *, int32_t, int32_t, const int32_t *, void *, void *);
+    int (*pad_chunks)(int32_t, const int32_t *, const int32_t *, const float *, const int32_t *, int32_t, int32_t, const int32_t *, void *, void *, int32_t);  // (ABI v5 builds ignore the trailing panel width)
     int (*row_lengths)(int32_t, const int32_t *, const int32_t *, int32_t *, void *);
     int (*build_aexp)(const spy_knn_args *, void *);
     int64_t (*scan_tmp)(int64_t);
@@ -165,7 +165,7 @@ int main(int argc, char **argv) {
             int32_t n_chunks = 0;
             CK(cudaMemcpy(&n_chunks, (int32_t *)d_cptr + n_seg, 4, cudaMemcpyDeviceToHost));
             CK(cudaMalloc(&d_chunks, (size_t)std::max(n_chunks, 1) * 16));
-            if (!rc) rc = L.pad_chunks(R, a.b_indptr, a.b_indices, a.b_data, a.b_split, a.split_stride, a.n_panels, (const int32_t *)d_cptr, d_chunks, nullptr);
+            if (!rc) rc = L.pad_chunks(R, a.b_indptr, a.b_indices, a.b_data, a.b_split, a.split_stride, a.n_panels, (const int32_t *)d_cptr, d_chunks, nullptr, a.panel_width);
             if (!rc) rc = L.row_lengths(n_t, a.targets, a.a_indptr, (int32_t *)d_cnt, nullptr);
             if (!rc) rc = L.scan64(n_t, (const int32_t *)d_cnt, (int64_t *)d_toff, d_tmp, nullptr);
             int64_t n_entries = 0;
@@ -227,12 +227,13 @@ int main(int argc, char **argv) {
             }
         }
         if (getenv("SPY_PROBE_PHASES") && a.engine == 2) {  // -DSPY_KS_TIMING builds: 24 cycle counters at the end of the scratch
-            unsigned long long ph[24];
+            unsigned long long ph[32];
             CK(cudaMemcpy(ph, (char *)d_scratch + sb - 256, sizeof(ph), cudaMemcpyDeviceToHost));
-            const char *names[24] = {"X snapshot", "X pass body", "X end-of-pass barrier", "X snapshot", "X wait drain", "X setup+first issue", "X passes", "",
-                                     "S snapshot", "S staging", "S end-of-pass barrier", "S snapshot", "S wait drain", "S setup", "S passes", "",
-                                     "D wait snapshot", "D sweep", "D forced selections", "D evaluate/tighten", "D final select+write", "D selections", "D slot batches", "D failed speculations"};
-            for (int i = 0; i < 24; i++) if (names[i][0]) printf("    %-24s %12.3f Mcycles per CTA%s\n", names[i], ph[i] / 148.0 / 1e6, (i % 8 == 6 || i == 21 || i == 23) ? " (count, in millions)" : "");
+            const char *names[32] = {"X snapshot (all)", "X pass body", "X end-of-pass barrier", "X snapshot copy", "X wait drain", "X setup+first issue", "X staging", "",
+                                     "Q snapshot (all)", "Q pass body", "Q end-of-pass barrier", "Q snapshot copy", "Q wait drain", "Q setup", "Q staging", "",
+                                     "D wait snapshot", "D sweep (all)", "D forced selections", "D evaluate/tighten", "D final select+write", "#D selections", "#D slot batches", "#D failed speculations",
+                                     "D speculative path", "D slot batches", "D tcgen05.ld", "#D quads queued", "#D carried bounds tried", "#D carried bounds failed", "", ""};
+            for (int i = 0; i < 32; i++) if (names[i][0] && ph[1] != 0) printf("    %-24s %12.3f %s\n", names[i], ph[i] / 148.0 / 1e6, names[i][0] == '#' ? "M per CTA (count)" : "Mcycles per CTA");
         }
         printf("%-44s %8.3f ms  %7.1f Gprod/s  engine %d (tables %.2f ms) panels %d x %d  threads %d group %d   rows differing from the first library: %ld\n",
                argv[li], best, products / best / 1e6, a.engine, prep_ms, a.n_panels, a.panel_width, a.threads, a.group, bad_rows);

@@ -641,7 +641,7 @@ class KnnJob:
                 n_chunks = int(chunk_indptr[-1].item()) if n_seg > 0 else 0
                 chunks = ctx.empty(max(n_chunks, 1) * 4, torch.int32)
                 _lib.check(lib.spy_knn_pad_chunks_dev(B.n_rows, _ptr(B.indptr), _ptr(B.indices), _ptr(B.data), split_ptr, stride, n_p,
-                                                      _ptr(chunk_indptr), _ptr(chunks), ctx.sptr))
+                                                      _ptr(chunk_indptr), _ptr(chunks), ctx.sptr, int(a.panel_width)))
                 return chunk_indptr, chunks
             chunk_indptr, chunks = B.cached(("chunks", int(a.panel_width), n_p), build_chunks)
             a.b_chunk_indptr, a.b_chunks = _ptr(chunk_indptr), _ptr(chunks)

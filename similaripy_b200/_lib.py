@@ -54,7 +54,7 @@ SIGNATURES = {
     "spy_knn_build_split_dev": (C.c_int, [_i32, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),
     "spy_knn_row_work_dev": (C.c_int, [_i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "spy_knn_chunk_counts_dev": (C.c_int, [_i32, _vp, _vp, _i32, _i32, _vp, _vp]),
-    "spy_knn_pad_chunks_dev": (C.c_int, [_i32, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
+    "spy_knn_pad_chunks_dev": (C.c_int, [_i32, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _i32]),
     "spy_knn_row_lengths_dev": (C.c_int, [_i32, _vp, _vp, _vp, _vp]),
     "spy_knn_build_aexp_dev": (C.c_int, [C.POINTER(KnnArgs), _vp]),
     "spy_knn_topk_dev": (C.c_int, [C.POINTER(KnnArgs), _vp, _i64, _vp]),
@@ -88,7 +88,7 @@ SIGNATURES = {
                                    C.c_int, C.c_int, _f64, _vp, _vp]),
 }
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 ENGINE_AUTO, ENGINE_FLAT, ENGINE_STREAM = 0, 1, 2
 ERR_UNSUPPORTED = -4
 ENGINES = {"auto": ENGINE_AUTO, "flat": ENGINE_FLAT, "stream": ENGINE_STREAM}

@@ -474,7 +474,7 @@ int spy_knn_topk_host(const spy_knn_args *host_args, int device) {
         if (rc != SPY_OK) { cleanup(); return rc; }
         if (!dev_alloc(&d_chunks, ((size_t)std::max(n_chunks, 1)) * 16)) { cleanup(); return SPY_ERR_NOMEM; }
         rc = spy_knn_pad_chunks_dev(a.b_rows, a.b_indptr, a.b_indices, a.b_data, a.b_split, a.split_stride, a.n_panels,
-                                    (const int32_t *)d_cptr, d_chunks, nullptr);
+                                    (const int32_t *)d_cptr, d_chunks, nullptr, a.panel_width);
         if (rc == SPY_OK) rc = spy_knn_row_lengths_dev(a.n_targets, a.targets, a.a_indptr, (int32_t *)d_len, nullptr);
         if (rc == SPY_OK) rc = spy_exclusive_scan_i64_dev(a.n_targets, (const int32_t *)d_len, (int64_t *)d_toff, d_tmp, nullptr);
         int64_t n_entries = 0;

@@ -28,7 +28,7 @@ __global__ void chunk_counts_kernel(int b_rows, const int *__restrict__ b_indptr
 // ends with the filler pair (0xffffffff, 0), which no panel accepts.
 __global__ void pad_chunks_kernel(int b_rows, const int *__restrict__ b_indptr, const int *__restrict__ b_indices,
                                   const float *__restrict__ b_data, const int *__restrict__ split, int split_stride,
-                                  int n_panels, const int *__restrict__ seg, uint2 *__restrict__ pairs_out) {
+                                  int n_panels, const int *__restrict__ seg, uint2 *__restrict__ pairs_out, int W) {
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
     const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -39,13 +39,22 @@ __global__ void pad_chunks_kernel(int b_rows, const int *__restrict__ b_indptr, 
             if (n_panels == 1) { s = b_indptr[u]; e = b_indptr[u + 1]; }
             else { s = split[(size_t)u * split_stride + pn]; e = split[(size_t)u * split_stride + pn + 1]; }
             uint2 *out = pairs_out + 2 * (size_t)seg[u * n_panels + pn];
+#if SPY_KS_LOCAL
+            // (byte offset of the accumulator slot inside the panel, value); the filler pair adds 0 to the spare slot behind
+            // the panel: the kernel's expansion loop has no test per product at all
+            const unsigned shift = 2u, base = (unsigned)pn * (unsigned)W;
+            const uint2 filler = make_uint2((unsigned)W * 4u, 0u);
+#else
+            const unsigned shift = 0u, base = 0u;
+            const uint2 filler = make_uint2(0xffffffffu, 0u);  // a column no panel accepts
+#endif
             for (int g0 = s; g0 < e; g0 += 64) {  // groups of 64 pairs: two per lane
                 const int q0 = g0 + lane, q1 = g0 + 32 + lane;
                 const bool v0 = q0 < e, v1 = q1 < e;
-                uint2 p0 = make_uint2(0xffffffffu, 0u), p1 = p0;
-                if (v0) p0 = make_uint2((unsigned)b_indices[q0], __float_as_uint(b_data[q0]));
-                if (v1) p1 = make_uint2((unsigned)b_indices[q1], __float_as_uint(b_data[q1]));
-                const int k0 = v0 ? (int)(p0.x & 31u) : 32, k1 = v1 ? (int)(p1.x & 31u) : 32;
+                uint2 p0 = filler, p1 = filler;
+                if (v0) p0 = make_uint2(((unsigned)b_indices[q0] - base) << shift, __float_as_uint(b_data[q0]));
+                if (v1) p1 = make_uint2(((unsigned)b_indices[q1] - base) << shift, __float_as_uint(b_data[q1]));
+                const int k0 = v0 ? (int)((p0.x >> shift) & 31u) : 32, k1 = v1 ? (int)((p1.x >> shift) & 31u) : 32;
                 int pos0 = 0, pos1 = 0;  // counting sort by bank: pairs of smaller banks first, then by position
                 for (int b = 0; b < 32; b++) {
                     const unsigned m0 = __ballot_sync(0xffffffffu, k0 == b), m1 = __ballot_sync(0xffffffffu, k1 == b);
@@ -58,7 +67,7 @@ __global__ void pad_chunks_kernel(int b_rows, const int *__restrict__ b_indptr, 
                 if (v0) out[(g0 - s) + pos0] = p0;
                 if (v1) out[(g0 - s) + pos1] = p1;
             }
-            if (((e - s) & 1) && lane == 0) out[e - s] = make_uint2(0xffffffffu, 0u);
+            if (((e - s) & 1) && lane == 0) out[e - s] = filler;
         }
     }
 }
@@ -214,13 +223,15 @@ int spy_knn_chunk_counts_dev(int32_t b_rows, const int32_t *b_indptr, const int3
 
 int spy_knn_pad_chunks_dev(int32_t b_rows, const int32_t *b_indptr, const int32_t *b_indices, const float *b_data,
                            const int32_t *b_split, int32_t split_stride, int32_t n_panels, const int32_t *chunk_indptr,
-                           void *chunks_out, void *stream) {
+                           void *chunks_out, void *stream, int32_t panel_width) {
     if (b_rows <= 0) return SPY_OK;
     SPY_REQUIRE(b_indptr && chunk_indptr && chunks_out && n_panels >= 1, "pad_chunks: bad arguments");
+    SPY_REQUIRE(panel_width > 0 && panel_width % 2048 == 0, "pad_chunks: panel_width of the stream plan missing");
     SPY_REQUIRE(n_panels == 1 || (b_split && split_stride >= n_panels + 1), "pad_chunks: n_panels > 1 needs b_split");
     const long long warps = std::min<long long>(b_rows, (long long)kB200SmCount * 64);
     pad_chunks_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, as_stream(stream)>>>(
-        b_rows, b_indptr, b_indices, b_data, b_split, split_stride, n_panels, chunk_indptr, reinterpret_cast<uint2 *>(chunks_out));
+        b_rows, b_indptr, b_indices, b_data, b_split, split_stride, n_panels, chunk_indptr, reinterpret_cast<uint2 *>(chunks_out),
+        panel_width);
     SPY_LAUNCH_OK();
     return SPY_OK;
 }

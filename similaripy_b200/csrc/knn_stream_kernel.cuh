@@ -56,6 +56,15 @@ struct KnnStreamDev {
 #ifndef SPY_KS_SPEC
 #define SPY_KS_SPEC 1  // speculative bound for a row's first panel (validated; see the drain)
 #endif
+#ifndef SPY_KS_SEARCH
+#define SPY_KS_SEARCH 1  // 1: segment of a chunk from a bit mask of segment starts (2 REDUX.OR per batch); 0: 5-step binary search by shuffles
+#endif
+#ifndef SPY_KS_LOCAL
+#define SPY_KS_LOCAL 1   // 1: chunks hold (byte offset of the slot inside its panel, value); 0: (column, value) -- see pad_chunks_kernel
+#endif
+#ifndef SPY_KS_HINT
+#define SPY_KS_HINT 1    // a row's first panel is swept with the bound the previous row's first panel validated (validated again)
+#endif
 #ifndef SPY_KS_PREFETCH
 #define SPY_KS_PREFETCH 0  // bulk L2 prefetch of the next pass's segments: measured slower (43.1 vs 40.4 ms, profiles/r02)
 #endif
@@ -89,7 +98,8 @@ struct KsMsg {    // what the expansion side hands to the drain with every snaps
 __host__ __device__ constexpr size_t ks_ring_bytes() { return SPY_KS_RING ? (size_t)KS_A_WARPS * 32 * KS_U * 16 : 0; }
 __host__ __device__ constexpr size_t ks_stage_bytes() { return (size_t)2 * (3 * KS_CH * 4 + 32 * 4); }
 __host__ __device__ constexpr size_t ks_queue_bytes() { return (size_t)KS_D_WARPS * KS_QCAP * (16 + 4); }
-__host__ __device__ constexpr size_t ks_fixed_bytes() { return ks_ring_bytes() + ks_stage_bytes() + ks_queue_bytes() + (size_t)KS_CAP * 8; }
+__host__ __device__ constexpr size_t ks_pad_bytes() { return SPY_KS_LOCAL ? 16 : 0; }  // the slot filler pairs are added to
+__host__ __device__ constexpr size_t ks_fixed_bytes() { return ks_pad_bytes() + ks_ring_bytes() + ks_stage_bytes() + ks_queue_bytes() + (size_t)KS_CAP * 8; }
 
 // ---- PTX helpers --------------------------------------------------------------------------------------------
 __device__ __forceinline__ void ks_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
@@ -281,7 +291,7 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const KnnDev &q = p.q;
     float *acc = reinterpret_cast<float *>(smem_raw);
-    unsigned char *ptr = smem_raw + (size_t)q.W * sizeof(float);
+    unsigned char *ptr = smem_raw + (size_t)q.W * sizeof(float) + ks_pad_bytes();
     const unsigned ring32 = (unsigned)__cvta_generic_to_shared(ptr);
     ptr += ks_ring_bytes();
     // staged pass (double buffered): per entry the chunk count prefix INSIDE its block of 32 entries, the first chunk, the
@@ -305,7 +315,7 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 #if SPY_KS_TIMING
-    long long kt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long kt[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 #endif
     const float sentinel = __uint_as_float(kSentinelBits);
     const float4 sentinel4 = make_float4(sentinel, sentinel, sentinel, sentinel);
@@ -383,9 +393,22 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
                 if (lane >= o) inc += u;
             }
             unsigned *st = stage0 + buf * KS_STAGE_WORDS;
+#if SPY_KS_SEARCH
+            // only the segments that hold chunks are staged, packed to the front of the block: every staged segment then
+            // starts at a chunk number of its own (the expansion finds a chunk's segment from a bit mask of the starts).
+            // Per segment: chunks before it inside the block; (first chunk in `chunks`) - that prefix; the entry's value.
+            // Per block: chunk total | staged segments << 26  (a block holds at most 32 x 32768 chunks).
+            const unsigned nm = __ballot_sync(0xffffffffu, c != 0u);
+            if (c != 0u) {
+                const int i = b * 32 + __popc(nm & ((1u << lane) - 1u));
+                st[i] = inc - c; st[KS_CH + i] = se.x - (inc - c); st[2 * KS_CH + i] = __float_as_uint(v);
+            }
+            if (lane == 31) st[3 * KS_CH + b] = inc | ((unsigned)__popc(nm) << 26);
+#else
             const int i = b * 32 + lane;
             st[i] = inc - c; st[KS_CH + i] = se.x; st[2 * KS_CH + i] = __float_as_uint(v);
             if (lane == 31) st[3 * KS_CH + b] = inc;
+#endif
         };
         auto stage_fetch = [&](const KsPass &d, int b, uint2 &se, float &v) {
             const int i = b * 32 + lane;
@@ -412,11 +435,9 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
         // ---- expansion warp state ----
         const unsigned slot32 = ring32 + (unsigned)((max(wa, 0) * 32 * KS_U + lane) * 16);  // chunk r of a batch: + r * 512
         unsigned f = 0u, fb = 0u, F1 = 0u;  // next chunk to issue, end of the sub-batch, end of the warp's range (uniform)
-        int j0 = 0, n_cur = 0;
-        unsigned boff = 0u, total = 0u;      // lane b: chunks before block b of the pass; chunks of the pass
-        unsigned Pe = 0u, Pi = 0u, C0 = 0u;  // lane l: segment j0 + l of the pass: first chunk number, end, first chunk in `chunks`
+        unsigned total = 0u;                // chunks of the pass
         float V = 0.f;
-        const unsigned *cP = nullptr;  // staged pass: prefixes; first chunks at + KS_CH, values at + 2 KS_CH
+        const unsigned *cP = nullptr;  // staged pass
         float vp[KS_U];
         unsigned lp = 0u;
 #if !SPY_KS_RING
@@ -426,6 +447,59 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
 #endif
 #pragma unroll
         for (int r = 0; r < KS_U; r++) vp[r] = 0.f;
+#if SPY_KS_SEARCH
+        // The window of an expansion warp is one staged BLOCK (up to 32 segments, all of them non-empty): lane l holds
+        // segment l of the block.  A batch covers the chunk numbers [f, f + 32 KS_U); the segments that START inside it set
+        // one bit each (distinct, because no staged segment is empty), one REDUX.OR per 32 chunks collects them, and the
+        // segment of chunk number f + x is  jprev + popc(starts at or before x),  jprev = the last segment that starts
+        // before f.  Two warp reductions per batch instead of ten dependent shuffles of a binary search.
+        unsigned bw = 0u;                   // lane b: chunks of the pass up to and including block b | staged segments of block b << 26
+        unsigned Pe = 0xffffffffu, Dl = 0u; // lane l: first chunk number of segment l of the block; (its first chunk in `chunks`) - Pe
+        int jprev = -1;
+        auto issue = [&]() {  // one batch of KS_U chunks per lane into the ring
+            if (f >= fb) {    // the block that holds chunk f (uniform); f < F1 <= total: it exists
+                const int blk = __ffs(__ballot_sync(0xffffffffu, (bw & 0x3ffffffu) > f)) - 1;
+                const unsigned wb = __shfl_sync(0xffffffffu, bw, blk), wp = __shfl_sync(0xffffffffu, bw, max(blk - 1, 0));
+                const unsigned bend = wb & 0x3ffffffu, bo = blk > 0 ? (wp & 0x3ffffffu) : 0u;
+                const unsigned *sb = cP + blk * 32 + lane;
+                Pe = 0xffffffffu;
+                if (lane < (int)(wb >> 26)) { Pe = bo + sb[0]; Dl = sb[KS_CH] - bo; V = __uint_as_float(sb[2 * KS_CH]); }
+                fb = min(F1, bend);
+                jprev = __popc(__ballot_sync(0xffffffffu, Pe < f)) - 1;
+            }
+            const unsigned s = Pe - f;  // (segments that start before f, and unused lanes: far beyond the batch)
+            const unsigned le = (2u << lane) - 1u;
+            int cum = jprev;
+            lp = 0u;
+#pragma unroll
+            for (int r = 0; r < KS_U; r++) {
+                unsigned bit;
+                asm("shl.b32 %0, %1, %2;" : "=r"(bit) : "r"(1u), "r"(s - 32u * (unsigned)r));  // (shift amounts above 31 give 0)
+                const unsigned M = __reduce_or_sync(0xffffffffu, bit);
+                const int j = cum + __popc(M & le);
+                cum += __popc(M);
+                const unsigned fr = f + (unsigned)(r * 32 + lane);
+                const unsigned dj = __shfl_sync(0xffffffffu, Dl, j);
+                vp[r] = __shfl_sync(0xffffffffu, V, j);
+                if (fr < fb) {
+#if SPY_KS_RING
+                    ks_cp_async16(slot32 + (unsigned)r * 512u, p.chunks + (dj + fr));
+#else
+                    nx[r] = __ldg(p.chunks + (dj + fr));
+#endif
+                    lp |= 1u << r;
+                }
+            }
+#if SPY_KS_RING
+            ks_cp_commit();
+#endif
+            jprev = cum;
+            f = min(f + 32u * KS_U, fb);
+        };
+#else
+        int j0 = 0, n_cur = 0;
+        unsigned boff = 0u;                  // lane b: chunks before block b of the pass
+        unsigned Pe = 0u, Pi = 0u, C0 = 0u;  // lane l: segment j0 + l of the pass: first chunk number, end, first chunk in `chunks`
         auto prefix_at = [&](int idx) -> unsigned {  // chunks of the pass before segment idx (all lanes call it together)
             const unsigned o = __shfl_sync(0xffffffffu, boff, min(idx, KS_CH - 1) >> 5);
             return idx >= n_cur ? total : cP[idx] + o;
@@ -467,10 +541,16 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
 #endif
             f = min(f + 32u * KS_U, fb);
         };
+#endif
+
+        // the panel's shared address, held in a register: as a known constant it is rebuilt from the CTA's rank in front of
+        // every add (S2UR / UMOV / UIADD3 / ULEA, a sixth of the instructions of the expansion loop)
+        unsigned accl = acc32;
+        asm volatile("add.u32 %0, %0, %1;" : "+r"(accl) : "r"((unsigned)q.n_targets >> 31));
 
         // ---- snapshot bookkeeping (uniform over the warps of the side) ----
         unsigned seq = 0u;  // snapshots / messages posted so far
-        bool pending = false, panel_landed = false, m_landed = false;
+        bool panel_landed = false, m_landed = false;
         auto post = [&](int t, int i_out, int pn, int flags, int landed) {  // one thread: message + "snapshot full"
             KsMsg *m = &s_msg[seq & 1u];
             m->t = t; m->i_out = i_out; m->pn = pn; m->flags = flags; m->landed = landed;
@@ -511,6 +591,47 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
             KS_ACC(3, ts);
         };
 
+        // set-up of a staged pass (buffer buf): the chunk range of this warp and its first batch; true: the warp has chunks
+        auto setup = [&](const KsPass &d, int buf) -> bool {
+            // chunks before every block of the pass (lane b: block b) and the pass total
+            const unsigned *st = stage0 + buf * KS_STAGE_WORDS;
+#if SPY_KS_SEARCH
+            const unsigned w = st[3 * KS_CH + lane], bt = w & 0x3ffffffu;
+#else
+            const unsigned bt = st[3 * KS_CH + lane];
+#endif
+            unsigned inc = bt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned v = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += v;
+            }
+            total = __shfl_sync(0xffffffffu, inc, 31);
+#if SPY_KS_SEARCH
+            bw = inc | (w & 0xfc000000u);
+            if (is_queue) return false;
+            cP = st;
+            const unsigned F0 = (unsigned)(((unsigned long long)total * (unsigned)wa) / KS_A_WARPS);
+            F1 = (unsigned)(((unsigned long long)total * (unsigned)(wa + 1)) / KS_A_WARPS);
+            f = F0; fb = F0;  // (the first issue loads the block of chunk F0)
+            if (F0 >= F1) return false;
+#else
+            boff = inc - bt;
+            if (is_queue) return false;
+            n_cur = d.n; cP = st;
+            const unsigned F0 = (unsigned)(((unsigned long long)total * (unsigned)wa) / KS_A_WARPS);
+            F1 = (unsigned)(((unsigned long long)total * (unsigned)(wa + 1)) / KS_A_WARPS);
+            f = F0; fb = F0;
+            if (F0 >= F1) return false;
+            // j0 = the last segment that starts at or before chunk F0: first its block, then inside the block
+            const int blk = __popc(__ballot_sync(0xffffffffu, lane * 32 <= n_cur && boff <= F0)) - 1;
+            const unsigned v = prefix_at(blk * 32 + lane);
+            j0 = blk * 32 + __popc(__ballot_sync(0xffffffffu, blk * 32 + lane <= n_cur && v <= F0)) - 1;
+#endif
+            issue();
+            return true;
+        };
+
         // ---- prologue: describe passes 0 and 1, stage pass 0 ----
         if (tid == KS_DT) {
             s_queue.have = 0;
@@ -525,7 +646,10 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
             else { stage_fetch(d0, wa, g_se, g_v); stage_block(0, wa, g_se, g_v); }
         }
         ks_bar_sync(1, KS_X_THREADS);
+        bool pending = false;
         KS_T0(tp);
+        // (A variant that set the next pass up BEFORE the end-of-pass barrier, with the pass descriptors three ahead and an
+        // mbarrier per staging buffer, was measured: equal on the probe, 161 vs 153 ms on configs[1] -- not kept.)
         for (int pass = 0;; pass++) {
             const int buf = pass & 1;
             const KsPass d = s_pass[pass & 3];
@@ -533,35 +657,10 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
             const bool stop = (d.flags & KS_FLAG_STOP) != 0;
             const bool stage_next = !stop && !(dn.flags & KS_FLAG_STOP);
             bool have = false;
-            unsigned base = 0u;
-            if (!stop) {
-                // chunks before every block of the pass (lane b: block b) and the pass total
-                const unsigned *st = stage0 + buf * KS_STAGE_WORDS;
-                const unsigned bt = st[3 * KS_CH + lane];
-                unsigned inc = bt;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const unsigned v = __shfl_up_sync(0xffffffffu, inc, o);
-                    if (lane >= o) inc += v;
-                }
-                boff = inc - bt;
-                total = __shfl_sync(0xffffffffu, inc, 31);
-                if (!is_queue) {  // this warp's chunk range of the pass and its first batch
-                    n_cur = d.n; cP = st;
-                    base = (unsigned)d.pn * (unsigned)q.W;
-                    const unsigned F0 = (unsigned)(((unsigned long long)total * (unsigned)wa) / KS_A_WARPS);
-                    F1 = (unsigned)(((unsigned long long)total * (unsigned)(wa + 1)) / KS_A_WARPS);
-                    f = F0; fb = F0;
-                    if (F0 < F1) {
-                        // j0 = the last segment that starts at or before chunk F0: first its block, then inside the block
-                        const int blk = __popc(__ballot_sync(0xffffffffu, lane * 32 <= n_cur && boff <= F0)) - 1;
-                        const unsigned v = prefix_at(blk * 32 + lane);
-                        j0 = blk * 32 + __popc(__ballot_sync(0xffffffffu, blk * 32 + lane <= n_cur && v <= F0)) - 1;
-                        issue();
-                        have = true;
-                    }
-                }
-            }
+#if !SPY_KS_LOCAL
+            const unsigned base = (unsigned)d.pn * (unsigned)q.W;
+#endif
+            if (!stop) have = setup(d, buf);  // this warp's chunk range of the pass and its first batch
             if (stage_next && !is_queue) stage_fetch(dn, wa, g_se, g_v);  // pass + 1: the loads land during this pass
             if (is_queue && !stop) {
                 if (lane == 0) {  // pass + 2
@@ -592,12 +691,22 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
 #pragma unroll
                 for (int r = 0; r < KS_U; r++) {
                     if (lc & (1u << r)) {
+#if SPY_KS_LOCAL
+                        // pr.x / pr.z: byte offset of the slot inside the panel (a filler pair adds 0 to the slot behind it)
+#ifdef SPY_KS_NOADDS  // timing experiment: gathers only (results are wrong)
+                        if (pr[r].x + pr[r].z == 0x12345u) smem_add_f32(accl, vc[r]);
+#else
+                        smem_add_f32(accl + pr[r].x, __fmul_rn(__uint_as_float(pr[r].y), vc[r]));
+                        smem_add_f32(accl + pr[r].z, __fmul_rn(__uint_as_float(pr[r].w), vc[r]));
+#endif
+#else
                         const unsigned d0 = pr[r].x - base, d1 = pr[r].z - base;
 #ifdef SPY_KS_NOADDS  // timing experiment: gathers only (results are wrong)
-                        if (d0 + d1 == 0x12345u) smem_add_f32(acc32, vc[r]);
+                        if (d0 + d1 == 0x12345u) smem_add_f32(accl, vc[r]);
 #else
-                        if (d0 < (unsigned)q.W) smem_add_f32(acc32 + d0 * 4u, __fmul_rn(__uint_as_float(pr[r].y), vc[r]));
-                        if (d1 < (unsigned)q.W) smem_add_f32(acc32 + d1 * 4u, __fmul_rn(__uint_as_float(pr[r].w), vc[r]));
+                        if (d0 < (unsigned)q.W) smem_add_f32(accl + d0 * 4u, __fmul_rn(__uint_as_float(pr[r].y), vc[r]));
+                        if (d1 < (unsigned)q.W) smem_add_f32(accl + d1 * 4u, __fmul_rn(__uint_as_float(pr[r].w), vc[r]));
+#endif
 #endif
                     }
                 }
@@ -651,6 +760,10 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
         u64 tau = 0ull;
         float lo = reject_bound(q, tau);
         int n_eval = 0;  // cand[0, n_eval) evaluated keys, cand[n_eval, s_cnt) raw candidates
+#if SPY_KS_HINT
+        float hint = 0.f;      // speculative bound (a similarity value) carried from row to row of this CTA; uniform
+        bool hint_ok = false;
+#endif
         // exact values of the raw candidates (computeSimilarity, s_plus.h:129-156; threshold, s_plus.h:206)
         auto evaluate = [&](int cnt) {
             for (int i = n_eval + dtid; i < cnt; i += KS_DT) {
@@ -734,6 +847,7 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
                     const float lc = lo_u * (KIND == KIND_D ? fr.cD : fr.cC), la = lo_u * fr.A0;
                     // per-slot test of up to 32 queued quads, all lanes busy: one L2 round trip for the batch; false = buffer full
                     auto batch = [&]() -> bool {
+                        KS_T0(tb);
                         __syncwarp();
                         const int nb = min(qn, 32);
                         const int e = qn - nb + lane;  // take from the end of the queue
@@ -768,6 +882,7 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
                             pos = __shfl_sync(0xffffffffu, pos, 31);
                             if (pos + tot > KS_CAP) {  // does not fit: dead fillers, select, come back (the quads stay queued)
                                 for (int i = pos + lane; i < min(pos + tot, KS_CAP); i += 32) cand[i] = 0xffffffffull;
+                                KS_ACC(9, tb);
                                 return false;
                             }
                             int w = pos + inc - c;
@@ -778,10 +893,11 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
                         }
                         qn -= nb;
                         KS_CNT(6, 1);
+                        KS_ACC(9, tb);
                         return true;
                     };
-                    // coarse test of one tile: quads that cannot be rejected as a whole join the queue
-                    auto tile = [&](int T, const float4 x) {
+                    // coarse test of one quad: false = no slot of it can enter the result
+                    auto quad_pass = [&](const float4 x) -> bool {
                         // (an untouched slot holds -0.0f: it fails x >= bound for every bound > 0)
                         bool pass = (x.x >= bound) | (x.y >= bound) | (x.z >= bound) | (x.w >= bound);
                         if (bound <= 0.f || !(KIND == KIND_RAW || KIND == KIND_C || KIND == KIND_D)) {
@@ -792,6 +908,10 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
                             if (bound <= 0.f) pass = touched;
                             else pass = (pass | (x.x < 0.f) | (x.y < 0.f) | (x.z < 0.f) | (x.w < 0.f)) & touched;
                         }
+                        return pass;
+                    };
+                    // one tile: quads that cannot be rejected as a whole join the queue
+                    auto tile = [&](int T, const float4 x, const bool pass) {
                         const unsigned bal = __ballot_sync(0xffffffffu, pass);
                         if (pass) {
                             const int e = qn + __popc(bal & ((1u << lane) - 1u));
@@ -799,6 +919,7 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
                             qc[e] = base + 512 * T + 128 * quarter + 4 * lane;
                         }
                         qn += __popc(bal);
+                        KS_CNT(11, __popc(bal));
                     };
                     while (!overflow && qn >= 32)  // (a round that follows an overflow starts with a full queue)
                         if (!batch()) overflow = true;
@@ -811,18 +932,27 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
                             ks_tmem_ld16(tmem_q + (unsigned)(16 * grp), xr);
                             const float4 x = i == 0 ? make_float4(xr[0], xr[1], xr[2], xr[3]) : i == 1 ? make_float4(xr[4], xr[5], xr[6], xr[7])
                                            : i == 2 ? make_float4(xr[8], xr[9], xr[10], xr[11]) : make_float4(xr[12], xr[13], xr[14], xr[15]);
-                            tile(4 * grp + i, x);
+                            tile(4 * grp + i, x, quad_pass(x));
                             gi = 1;
                         }
                     } else
                     for (; gi < nGloc && !overflow; gi++) {
                         const int grp = dsub + DPQ * gi;
                         float xr[16];
+                        KS_T0(tl);
                         ks_tmem_ld16(tmem_q + (unsigned)(16 * grp), xr);
+                        KS_ACC(10, tl);
+                        // the four tiles of the group are tested at once -- sixteen independent compares and ONE vote when no quad
+                        // of the warp passes (the usual case once a bound exists); the drain warps share their schedulers with
+                        // six expansion warps each, so that every dependent instruction of the sweep is expensive
+                        bool ps[4];
+#pragma unroll
+                        for (int i = 0; i < 4; i++) ps[i] = quad_pass(make_float4(xr[4 * i], xr[4 * i + 1], xr[4 * i + 2], xr[4 * i + 3]));
+                        if (i_res == 0 && !__any_sync(0xffffffffu, ps[0] | ps[1] | ps[2] | ps[3])) continue;
 #pragma unroll
                         for (int i = 0; i < 4; i++) {
                             if (i >= i_res && !overflow) {
-                                tile(4 * grp + i, make_float4(xr[4 * i], xr[4 * i + 1], xr[4 * i + 2], xr[4 * i + 3]));
+                                tile(4 * grp + i, make_float4(xr[4 * i], xr[4 * i + 1], xr[4 * i + 2], xr[4 * i + 3]), ps[i]);
                                 if (qn >= 32 && !batch()) { overflow = true; i_res = i + 1; }
                             }
                         }
@@ -848,7 +978,49 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
                 // and sweep with it.  The snapshot is read-only, so the bound is simply VALIDATED afterwards (k buffered
                 // candidates beat it) and the panel swept again without it if it is not: results never depend on the sample.
                 bool done = false;
+                KS_T0(tsp);
+                // sweep with the speculative bound tau_s, evaluate, count the buffered candidates that beat it (uniform)
+                auto try_bound = [&](u64 tau_s) -> int {
+                    sweep(reject_bound(q, tau_s), false);
+                    const int c2 = min(*reinterpret_cast<volatile int *>(&s_cnt), KS_CAP);
+                    evaluate(c2);
+                    if (dtid == 0) s_live = 0;
+                    ks_dsync();
+                    int above = 0;
+                    for (int i = dtid; i < c2; i += KS_DT) above += cand[i] > tau_s ? 1 : 0;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) above += __shfl_xor_sync(0xffffffffu, above, o);
+                    if (lane == 0 && above) atomicAdd(&s_live, above);
+                    ks_dsync();
+                    above = *reinterpret_cast<volatile int *>(&s_live);
+                    ks_dsync();
+                    return above;
+                };
+                auto forget = [&]() {  // not validated: forget what was buffered; the valid bound is none again
+                    if (dtid == 0) s_cnt = 0;
+                    n_eval = 0; tau = 0ull; lo = reject_bound(q, tau);
+                    ks_dsync();
+                };
                 if (SPY_KS_SPEC && filter && tau == 0ull && n_eval == 0 && nG >= 2 * DPQ) {  // (uniform over the drain warps)
+#if SPY_KS_HINT
+                    // (a) the bound that the first panel of this CTA's previous row validated: consecutive rows of one matrix
+                    //     look alike, and a wrong guess only costs the sweep that finds it out
+                    if (hint_ok) {
+                        const u64 tau_h = (u64)ordered_bits(hint) << 32;
+                        const int above = try_bound(tau_h);
+                        done = above >= q.k;
+                        KS_CNT(12, 1);
+                        if (done) {  // keep the bound where about 2 k candidates of a first panel beat it
+                            if (above > 3 * q.k) hint += 0.08f * fabsf(hint);
+                            else if (2 * above < 3 * q.k) hint -= 0.05f * fabsf(hint);
+                        }
+                        else { forget(); hint_ok = false; KS_CNT(13, 1); }
+                    }
+                    if (!done) {
+#else
+                    {
+#endif
+                    // (b) a bound from a sample of this panel
                     sweep(0.f, true);
                     const int cnt = min(*reinterpret_cast<volatile int *>(&s_cnt), KS_CAP);
                     evaluate(cnt);
@@ -868,27 +1040,19 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
                     n_eval = 0;
                     ks_dsync();
                     if (tau_s != 0ull) {
-                        sweep(reject_bound(q, tau_s), false);
-                        const int c2 = min(*reinterpret_cast<volatile int *>(&s_cnt), KS_CAP);
-                        evaluate(c2);
-                        if (dtid == 0) s_live = 0;
-                        ks_dsync();
-                        int above = 0;
-                        for (int i = dtid; i < c2; i += KS_DT) above += cand[i] > tau_s ? 1 : 0;
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) above += __shfl_xor_sync(0xffffffffu, above, o);
-                        if (lane == 0 && above) atomicAdd(&s_live, above);
-                        ks_dsync();
-                        done = *reinterpret_cast<volatile int *>(&s_live) >= q.k;
-                        ks_dsync();
+                        done = try_bound(tau_s) >= q.k;
                         KS_CNT(7, done ? 0 : 1);
-                        if (!done) {  // not validated: forget what was buffered, sweep again with the valid bound (none)
-                            if (dtid == 0) s_cnt = 0;
-                            n_eval = 0; tau = 0ull; lo = reject_bound(q, tau);
-                            ks_dsync();
-                        }
+                        if (!done) forget();
+#if SPY_KS_HINT
+                        else { hint = unordered_bits((unsigned)(tau_s >> 32)); hint_ok = true; }
+#ifdef SPY_HINT_STRESS  // test builds: a carried bound that is (almost) never valid, to exercise its failure path
+                        hint = 8.f * fabsf(hint) + 1.f;
+#endif
+#endif
+                    }
                     }
                 }
+                KS_ACC(8, tsp);
                 if (!done) sweep(0.f, false);
             }
             KS_ACC(1, td);
@@ -933,7 +1097,9 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
 #if SPY_KS_TIMING
         // drain warp 0 -> 16..22: [0] wait for a snapshot  [1] sweep  [2] selections forced by a full buffer  [3] evaluate / tighten
         // [4] final selection + write  [5] selections  [6] per-slot batches
-        if (tid == 0) for (int i = 0; i < 8; i++) atomicAdd(q.phase + 16 + i, (u64)kt[i]);  // [7] speculative bounds that failed validation
+        // [8] speculative path (sample, bound, sweep, validation)  [9] per-slot batches  [10] tcgen05.ld of the sweeps  [11] quads queued
+        // [12] rows that tried the carried bound  [13] ... and failed
+        if (tid == 0) for (int i = 0; i < 16; i++) atomicAdd(q.phase + 16 + i, (u64)kt[i]);  // [7] speculative bounds that failed validation
 #endif
     }
     ks_tc_fence_before();
