@@ -233,7 +233,7 @@ int main(int argc, char **argv) {
                                      "Q snapshot (all)", "Q pass body", "Q end-of-pass barrier", "Q snapshot copy", "Q wait drain", "Q setup", "Q staging", "",
                                      "D wait snapshot", "D sweep (all)", "D forced selections", "D evaluate/tighten", "D final select+write", "#D selections", "#D slot batches", "#D failed speculations",
                                      "D speculative path", "D slot batches", "D tcgen05.ld", "#D quads queued", "#D carried bounds tried", "#D carried bounds failed", "", ""};
-            for (int i = 0; i < 32; i++) if (names[i][0] && ph[1] != 0) printf("    %-24s %12.3f %s\n", names[i], ph[i] / 148.0 / 1e6, names[i][0] == '#' ? "M per CTA (count)" : "Mcycles per CTA");
+            for (int i = 0; i < 32; i++) if (names[i][0] && ph[1] != 0) printf("    %-26s %12.3f %s\n", names[i], ph[i] / 148.0 / (names[i][0] == '#' ? 1e3 : 1e6), names[i][0] == '#' ? "k per CTA (count)" : "Mcycles per CTA");
         }
         printf("%-44s %8.3f ms  %7.1f Gprod/s  engine %d (tables %.2f ms) panels %d x %d  threads %d group %d   rows differing from the first library: %ld\n",
                argv[li], best, products / best / 1e6, a.engine, prep_ms, a.n_panels, a.panel_width, a.threads, a.group, bad_rows);
