@@ -125,7 +125,9 @@ typedef struct spy_knn_args {
     const int32_t *row_order;   /* optional permutation of [0,n_targets): processing order  */
     int64_t b_nnz;              /* stored entries of B (b_indptr[b_rows]); 0 = unknown: only used to
                                  * size `group` from the mean segment length                      */
-    int32_t group;              /* lanes streaming one B-row segment together: 4, 8, 16 or 32      */
+    int32_t group;              /* flat engine: lanes streaming one B-row segment together (4, 8, 16 or 32);
+                                 * stream engine: drain warps of the CTA -- 8, or 16 for target rows with few
+                                 * products per panel; 0 = let spy_knn_plan choose (it returns the choice here) */
     /* kernel generation: 0 = let spy_knn_plan choose, SPY_ENGINE_FLAT = knn_flat_kernel (expansion and drain
      * alternate; every configuration), SPY_ENGINE_STREAM = knn_stream_kernel (cp.async ring, the panel is
      * snapshotted into tensor memory and drained concurrently; needs the three tables below) */

@@ -610,9 +610,13 @@ class KnnJob:
         prefer = self.tuning.get("engine_prefer") if not eng else None
         want = prefer if prefer is not None else eng
         a.engine = _lib.ENGINES[want] if isinstance(want, str) else int(want)
+        # "drain_warps": 8 or 16, the build of the stream kernel (default: the planner's choice from the products per panel)
+        if a.engine == _lib.ENGINE_STREAM and self.tuning.get("drain_warps"):
+            a.group = int(self.tuning["drain_warps"])
         rc = lib.spy_knn_plan(C.byref(a), ctx.index)
         if rc == _lib.ERR_UNSUPPORTED and prefer is not None:
             a.engine = _lib.ENGINE_AUTO if _lib.ENGINES.get(prefer, prefer) == _lib.ENGINE_FLAT else _lib.ENGINE_FLAT
+            a.group = int(self.tuning.get("group", 0))
             rc = lib.spy_knn_plan(C.byref(a), ctx.index)
         _lib.check(rc)
         if a.n_panels > 1:

@@ -15,9 +15,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 LIB = os.path.join(PKG, "libsimilaripy_b200.so")
-SOURCES = ("api.cu", "knn_kernel.cu", "knn_stream.cu", "knn_inst_g4.cu", "knn_inst_g8.cu", "knn_inst_g16.cu", "knn_inst_g32.cu",
+SOURCES = ("api.cu", "knn_kernel.cu", "knn_stream.cu", "knn_stream_sparse.cu", "knn_inst_g4.cu", "knn_inst_g8.cu", "knn_inst_g16.cu", "knn_inst_g32.cu",
            "csr_ops.cu", "normalize.cu", "host_api.cu", "knn_reforder.cu")
-HEADERS = ("common.cuh", "knn_kernel.cuh", "knn_stream_kernel.cuh", "knn_inst.inc", os.path.join("..", "..", "include", "similaripy_b200.h"))
+HEADERS = ("common.cuh", "knn_kernel.cuh", "knn_stream_kernel.cuh", "knn_stream_impl.inc", "knn_inst.inc", os.path.join("..", "..", "include", "similaripy_b200.h"))
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default", "--use_fast_math=false",

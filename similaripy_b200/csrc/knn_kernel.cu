@@ -90,8 +90,25 @@ static int similarity_kind(const spy_knn_args &a, int &exact_only);
 static int choose_engine(const spy_knn_args &a, int max_smem_optin, StreamPlan &sp) {
     int exact_only = 0;
     similarity_kind(a, exact_only);
+    // Which build of the stream kernel: 8 drain warps + 24 on the expansion side, or 16 + 16 for target rows with few scalar
+    // products per panel, where the sweep of the panel and the selections are the critical path (configs[4]-shaped
+    // operands, 4e3 products per panel: 34.2 vs 40.0 ms; configs[3]-shaped, 1.9e4: 33.1 vs 28.9 ms; profiles/r02).
+    // args.group = 8 / 16 asks for one of them (spy_knn_plan returns the choice there); SPY_KS_DRAIN=8|16 overrides.
+    int drain = (a.engine == SPY_ENGINE_STREAM && (a.group == stream_drain_warps(false) || a.group == stream_drain_warps(true))) ? a.group : 0;
+    if (drain == 0) {
+        static const int env = [] { const char *e = getenv("SPY_KS_DRAIN"); return e ? atoi(e) : 0; }();
+        if (env == stream_drain_warps(false) || env == stream_drain_warps(true)) drain = env;
+    }
+    if (drain == 0) {
+        drain = stream_drain_warps(false);
+        if (a.a_nnz > 0 && a.b_nnz > 0 && a.a_rows > 0 && a.b_rows > 0) {
+            const int panels_est = std::max(1, (std::max(a.n_cols, 1) + 40959) / 40960);
+            const double per_panel = ((double)a.a_nnz / a.a_rows) * ((double)a.b_nnz / a.b_rows) / panels_est;
+            if (per_panel < 8192.0) drain = stream_drain_warps(true);
+        }
+    }
     const bool eligible = !exact_only && a.target_mode != SPY_SEL_MATRIX && (a.threads == 0 || a.threads == 1024) &&
-                          stream_plan(a.k, a.n_cols, a.engine == SPY_ENGINE_STREAM ? a.panel_width : 0, max_smem_optin, sp);
+                          stream_plan(a.k, a.n_cols, a.engine == SPY_ENGINE_STREAM ? a.panel_width : 0, max_smem_optin, drain, sp);
     int want = a.engine;
     if (want == SPY_ENGINE_AUTO) {
         static const int env = [] {
@@ -101,14 +118,9 @@ static int choose_engine(const spy_knn_args &a, int max_smem_optin, StreamPlan &
             return SPY_ENGINE_AUTO;
         }();
         want = env != SPY_ENGINE_AUTO ? env : SPY_ENGINE_DEFAULT;
+        // (Round 2 kept short rows on the flat engine; with the 16-drain-warp build the stream engine is ahead there too:
+        // 31.1 vs 40.9 ms at 1e3 products per panel, 34.2 vs 44.1 ms at 4e3.)
         if (want == SPY_ENGINE_STREAM && !eligible) want = SPY_ENGINE_FLAT;
-        // Short rows: the stream engine pays a snapshot + a sweep of the whole panel per (row, panel) whatever the row
-        // holds; below ~W/8 scalar products per panel the flat engine is faster (configs[4]: 4e3 products per panel,
-        // flat 50.8 vs stream 40.7 Gproducts/s, profiles/r02).
-        if (want == SPY_ENGINE_STREAM && env == SPY_ENGINE_AUTO && a.a_nnz > 0 && a.b_nnz > 0 && a.a_rows > 0 && a.b_rows > 0) {
-            const double per_panel = ((double)a.a_nnz / a.a_rows) * ((double)a.b_nnz / a.b_rows) / std::max(sp.n_panels, 1);
-            if (per_panel < sp.W / 8.0) want = SPY_ENGINE_FLAT;
-        }
     }
     if (want == SPY_ENGINE_STREAM && !eligible) return -1;
     return want;
@@ -127,7 +139,7 @@ static int make_plan(const spy_knn_args &a, int device, Plan &pl) {
         return SPY_ERR_UNSUPPORTED;
     }
     if (pl.engine == SPY_ENGINE_STREAM) {
-        pl.threads = KS_NT; pl.ctas_per_sm = 1; pl.cap = pl.stream.cap; pl.cand_smem = true; pl.group = 32;
+        pl.threads = KS_NT; pl.ctas_per_sm = 1; pl.cap = pl.stream.cap; pl.cand_smem = true; pl.group = pl.stream.drain_warps;
         pl.W = pl.stream.W; pl.n_panels = pl.stream.n_panels; pl.smem_bytes = pl.stream.smem_bytes;
         int stride = pl.n_panels + 1;
         if (stride <= 8) { int q = 1; while (q < stride) q <<= 1; stride = q; }

@@ -105,104 +105,30 @@ __global__ void build_aexp_kernel(int n_targets, const int *__restrict__ targets
     }
 }
 
-// out[pn * 128 + l] = min of y over the columns TMEM lane l holds of panel pn: quads l, l + 128, ... of the panel's W
-// columns (the drain's coarse bound is one register per lane); +inf when the lane has no column inside the matrix
-__global__ void lane_min_kernel(int n_cols, int W, int n_panels, const float *__restrict__ y, float *__restrict__ out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_panels * 128) return;
-    const int pn = i >> 7, l = i & 127;
-    float m = __int_as_float(0x7f800000);
-    for (int c0 = pn * W + 4 * l; c0 < min(n_cols, (pn + 1) * W); c0 += 512)
-        for (int c = c0; c < min(n_cols, c0 + 4); c++) m = fminf(m, y[c]);
-    out[i] = m;
+}  // namespace spy
+
+#include "knn_stream_impl.inc"
+
+// the two builds of the kernel (this translation unit: `a`; knn_stream_sparse.cu: `b`)
+namespace spy {
+bool stream_plan_b(int k, int n_cols, int panel_width, int max_smem_optin, StreamPlan &sp);
+int stream_drain_warps_b();
+int stream_launch_b(const spy_knn_args &a, const StreamPlan &sp, int kind, int exact_only, int grid, void *scratch,
+                    int64_t scratch_bytes, cudaStream_t st);
+
+int stream_drain_warps(bool sparse) { return sparse ? stream_drain_warps_b() : stream_drain_warps_a(); }
+bool stream_plan(int k, int n_cols, int panel_width, int max_smem_optin, int drain_warps, StreamPlan &sp) {
+    if (drain_warps == stream_drain_warps_b() && drain_warps != stream_drain_warps_a())
+        return stream_plan_b(k, n_cols, panel_width, max_smem_optin, sp);
+    return stream_plan_a(k, n_cols, panel_width, max_smem_optin, sp);
 }
-
-bool stream_plan(int k, int n_cols, int panel_width, int max_smem_optin, StreamPlan &sp) {
-    sp.cap = KS_CAP;
-    if (2 * std::max(k, 1) > KS_CAP) return false;  // the candidate buffer holds k kept keys plus what one sweep step adds
-    const size_t fixed = ks_fixed_bytes();
-    const size_t budget = (size_t)max_smem_optin - 1024;  // static shared memory of the kernel (barriers, descriptors) + slack
-    if (budget <= fixed + 2048 * 4) return false;
-    int w_max = (int)((budget - fixed) / 4 / 2048) * 2048;  // whole groups of four 512-column tiles
-    w_max = std::min(w_max, 65536);  // 128 lanes x 512 columns of tensor memory
-    n_cols = std::max(n_cols, 1);
-    int W = panel_width;
-    if (W <= 0) {
-        const int P = ceil_div(n_cols, w_max);
-        W = ceil_div(ceil_div(n_cols, P), 2048) * 2048;
-    } else if (W % 2048 != 0 || W > w_max) return false;
-    sp.W = W;
-    sp.n_panels = ceil_div(n_cols, W);
-    sp.smem_bytes = (size_t)W * 4 + fixed;
-    return true;
-}
-
-static int64_t lm_bytes(int n_panels) { return (int64_t)std::max(n_panels, 1) * 128 * 4; }
-int64_t stream_scratch_bytes(int n_panels) { return 256 + 3 * lm_bytes(n_panels) + 256; }
-
-template <int KIND>
-static knn_stream_kernel_t stream_kernel() { return (knn_stream_kernel_t)knn_stream_kernel<KIND>; }
-
+int64_t stream_scratch_bytes(int n_panels) { return stream_scratch_bytes_a(n_panels); }  // (the same for both builds)
 int stream_launch(const spy_knn_args &a, const StreamPlan &sp, int kind, int exact_only, int grid, void *scratch,
                   int64_t scratch_bytes, cudaStream_t st) {
-    SPY_REQUIRE(a.b_chunks && a.b_chunk_indptr && a.toff, "stream engine: b_chunks / b_chunk_indptr / toff missing");
-    SPY_REQUIRE(a.n_entries == 0 || a.aexp, "stream engine: aexp missing (spy_knn_build_aexp_dev)");
-    SPY_REQUIRE(a.target_mode != SPY_SEL_MATRIX && !exact_only, "stream engine does not cover this configuration");
-    SPY_REQUIRE(scratch != nullptr && scratch_bytes >= stream_scratch_bytes(sp.n_panels), "scratch too small");
-    KnnStreamDev p;
-    KnnDev &d = p.q;
-    d.n_targets = a.n_targets; d.targets = a.targets; d.row_order = a.row_order;
-    d.a_indptr = a.a_indptr; d.a_indices = a.a_indices; d.a_data = a.a_data;
-    d.b_indptr = a.b_indptr; d.b_indices = a.b_indices; d.b_data = a.b_data;
-    d.b_pairs = nullptr; d.b_split = nullptr; d.split_stride = 0;
-    d.n_panels = sp.n_panels; d.W = sp.W; d.n_cols = a.n_cols;
-    d.Xt = a.Xtversky; d.Yt = a.Ytversky; d.Xc = a.Xcosine; d.Yc = a.Ycosine; d.Xd = a.Xdepop; d.Yd = a.Ydepop;
-    d.y_block_min = nullptr;
-    d.a1 = a.a1; d.l1 = a.l1; d.l2 = a.l2; d.l3 = a.l3; d.t1 = a.t1; d.t2 = a.t2;
-    d.stab = a.stabilized_shrink; d.bayes = a.bayesian_shrink; d.thr = a.threshold;
-    d.has_den = (a.l1 != 0.f || a.l2 != 0.f || a.l3 != 0.f || a.stabilized_shrink != 0.f || a.bayesian_shrink != 0.f) ? 1 : 0;
-    d.exact_only = exact_only;
-    d.k = a.k; d.cap = sp.cap; d.group = 0;
-    d.filter_mode = a.filter_mode; d.f_indptr = a.filter_indptr; d.f_indices = a.filter_indices;
-    d.target_mode = a.target_mode; d.t_indptr = a.target_indptr; d.t_indices = a.target_indices;
-    d.out_rows = a.out_rows; d.out_cols = a.out_cols; d.out_vals = a.out_values; d.out_counts = a.out_counts;
-    unsigned char *sc = reinterpret_cast<unsigned char *>(scratch);
-    d.work_counter = reinterpret_cast<int *>(sc);
-    d.phase = reinterpret_cast<u64 *>(sc + 256 + 3 * lm_bytes(sp.n_panels));  // SPY_KS_TIMING builds: 24 counters
-    d.cand_global = nullptr;
-    p.err = reinterpret_cast<int *>(sc + 64);
-    p.toff = reinterpret_cast<const long long *>(a.toff);
-    p.E = a.n_entries;
-    p.aexp = reinterpret_cast<const uint2 *>(a.aexp);
-    p.chunks = reinterpret_cast<const uint4 *>(a.b_chunks);
-    SPY_CUDA_OK(cudaMemsetAsync(scratch, 0, 256, st));
-    SPY_CUDA_OK(cudaMemsetAsync(sc + 256 + 3 * lm_bytes(sp.n_panels), 0, 256, st));
-    // minima of the Y vectors in use over the columns every TMEM lane holds of every panel: the drain's coarse bound
-    const int64_t lmb = lm_bytes(sp.n_panels);
-    p.ymin_t = p.ymin_c = p.ymin_d = nullptr;
-    const float *src[3] = {a.l1 != 0.f ? a.Ytversky : nullptr, a.l2 != 0.f ? a.Ycosine : nullptr, a.l3 != 0.f ? a.Ydepop : nullptr};
-    const float **dst[3] = {&p.ymin_t, &p.ymin_c, &p.ymin_d};
-    for (int i = 0; i < 3; i++) {
-        if (src[i] == nullptr || a.n_cols <= 0) continue;
-        float *lm = reinterpret_cast<float *>(sc + 256 + i * lmb);
-        lane_min_kernel<<<(sp.n_panels * 128 + 127) / 128, 128, 0, st>>>(a.n_cols, sp.W, sp.n_panels, src[i], lm);
-        SPY_LAUNCH_OK();
-        *dst[i] = lm;
-    }
-    knn_stream_kernel_t kern;
-    switch (kind) {
-    case KIND_RAW: kern = stream_kernel<KIND_RAW>(); break;
-    case KIND_T: kern = stream_kernel<KIND_T>(); break;
-    case KIND_C: kern = stream_kernel<KIND_C>(); break;
-    case KIND_D: kern = stream_kernel<KIND_D>(); break;
-    default: kern = stream_kernel<KIND_GEN>(); break;
-    }
-    SPY_CUDA_OK(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.smem_bytes));
-    kern<<<grid, KS_NT, sp.smem_bytes, st>>>(p);
-    SPY_LAUNCH_OK();
-    return SPY_OK;
+    if (sp.drain_warps == stream_drain_warps_b() && sp.drain_warps != stream_drain_warps_a())
+        return stream_launch_b(a, sp, kind, exact_only, grid, scratch, scratch_bytes, st);
+    return stream_launch_a(a, sp, kind, exact_only, grid, scratch, scratch_bytes, st);
 }
-
 }  // namespace spy
 
 using namespace spy;

@@ -31,7 +31,19 @@
 #pragma once
 #include "knn_kernel.cuh"
 
+// The kernel is compiled twice with different splits of the CTA's 32 warps between the drain and the expansion (knn_stream.cu:
+// 8 + 24; knn_stream_sparse.cu: 16 + 16 for target rows with few products per panel, where the drain is the critical
+// path).  Everything that depends on the split lives in an inline namespace named after the build, so that the two
+// translation units do not define the same symbols.
+#ifndef SPY_KS_TAG
+#define SPY_KS_TAG a
+#endif
+#define SPY_KS_CAT2(x, y) x##y
+#define SPY_KS_CAT(x, y) SPY_KS_CAT2(x, y)
+#define SPY_KS_INL SPY_KS_CAT(ks_, SPY_KS_TAG)
+
 namespace spy {
+inline namespace SPY_KS_INL {
 
 struct KnnStreamDev {
     KnnDev q;                // shared fields (targets, A, vectors, scalars, k, cap, selectors, outputs, work counter)
@@ -65,6 +77,15 @@ struct KnnStreamDev {
 #ifndef SPY_KS_HINT
 #define SPY_KS_HINT 1    // a row's first panel is swept with the bound the previous row's first panel validated (validated again)
 #endif
+#ifndef SPY_KS_REGSORT
+#define SPY_KS_REGSORT 1  // the exact selection sorts in registers (shuffles; shared memory only for strides of 32 and more)
+#endif
+#ifndef SPY_KS_REDUCE
+#define SPY_KS_REDUCE 0   // 1: a filling buffer is cut by sampled pivots only (no sort) -- measured 1 % slower with 8 drain warps
+#endif
+#ifndef SPY_KS_VECQ
+#define SPY_KS_VECQ 1    // the drain queues the passing quads of the four tiles of a group at once (0: tile by tile)
+#endif
 #ifndef SPY_KS_PREFETCH
 #define SPY_KS_PREFETCH 0  // bulk L2 prefetch of the next pass's segments: measured slower (43.1 vs 40.4 ms, profiles/r02)
 #endif
@@ -77,9 +98,11 @@ constexpr int KS_DT = KS_D_WARPS * 32;
 constexpr int KS_U = SPY_KS_U;                 // 16-byte chunks per lane per batch (ring: 16 * KS_U bytes per lane)
 constexpr int KS_CH = 1024;                    // entries of a target row per pass (32 blocks of 32)
 constexpr int KS_CAP = 1024;                   // candidate buffer (keys); k <= KS_CAP / 2
-constexpr int KS_QCAP = 64;                    // quads per drain warp waiting for their per-slot test
+constexpr int KS_S_WARPS = KS_D_WARPS < 8 ? KS_D_WARPS : 8;  // drain warps that take part in the sample of a first panel
+constexpr int KS_QBATCH = KS_D_WARPS > 8 ? 16 : 32;  // queued quads that trigger their per-slot test
+constexpr int KS_QCAP = KS_QBATCH + 32;          // quads per drain warp waiting for it (a tile adds up to 32)
 constexpr int KS_FLAG_PANEL_END = 1, KS_FLAG_ROW_END = 2, KS_FLAG_STOP = 4;
-static_assert(KS_D_WARPS == 4 || KS_D_WARPS == 8, "drain warps must cover whole lane quarters");
+static_assert(KS_D_WARPS % 4 == 0 && KS_D_WARPS >= 4 && KS_D_WARPS <= 16, "drain warps must cover whole lane quarters");
 
 struct KsPass {   // one pass = up to KS_CH entries of a target row against one panel (shared memory, ring of 4)
     long long aoff;  // first entry of the pass in aexp
@@ -183,8 +206,8 @@ static __device__ void ks_bitonic_desc(u64 *cand, int S, int dtid) {
 // 3 sigma below the sample quantile of the k-th best; the keys above it are compacted IN PLACE (every thread holds its
 // keys in registers across the barrier that separates the reads from the writes).  Returns the new n, or -1 when the
 // pivot was unlucky (fewer than k keys above it): nothing has been moved then.
-static __device__ int ks_pivot_round(u64 *cand, int n, int k, int j, int *s_wsum, u64 *s_pivot, int dtid) {
-    constexpr int KPT = KS_CAP / KS_DT;  // keys per thread
+static __device__ int ks_pivot_round(u64 *cand, int n, int k, int j, int *s_wsum, u64 *s_pivot, int dtid, u64 *pivot_out = nullptr) {
+    constexpr int KPT = (KS_CAP + KS_DT - 1) / KS_DT;  // keys per thread
     const int lane = dtid & 31, w = dtid >> 5;
     if (dtid < 32) {
         u64 k0 = cand[(int)(((long long)dtid * n) >> 6)];
@@ -211,6 +234,7 @@ static __device__ int ks_pivot_round(u64 *cand, int n, int k, int j, int *s_wsum
     }
     ks_dsync();
     const u64 pivot = *s_pivot;
+    if (pivot_out) *pivot_out = pivot;
     u64 kk[KPT];
     int cnt = 0;
 #pragma unroll
@@ -243,6 +267,68 @@ static __device__ int ks_pivot_round(u64 *cand, int n, int k, int j, int *s_wsum
     ks_dsync();
     return total >= k ? total : -1;
 }
+// Bitonic sort (descending) of cand[0, S) with the keys in REGISTERS (thread t holds keys t, t + KS_DT, ...): the steps with
+// a stride below 32 are warp shuffles, only the others go through shared memory (6 of the 36 steps of 256 keys) -- a step
+// through shared memory costs two barriers of the drain warps, and the drain's barriers are slow because its warps share
+// their schedulers with the expansion.
+template <int S>
+static __device__ __noinline__ void ks_sort_regs(u64 *cand, int dtid) {
+    constexpr int KPT = (S + KS_DT - 1) / KS_DT;
+    u64 kk[KPT];
+#pragma unroll
+    for (int r = 0; r < KPT; r++) {
+        const int i = r * KS_DT + dtid;
+        kk[r] = i < S ? cand[i] : 0ull;
+    }
+    for (int size = 2; size <= S; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            if (stride >= 32) {
+                ks_dsync();  // (the previous readers of cand are done)
+#pragma unroll
+                for (int r = 0; r < KPT; r++) {
+                    const int i = r * KS_DT + dtid;
+                    if (i < S) cand[i] = kk[r];
+                }
+                ks_dsync();
+            }
+#pragma unroll
+            for (int r = 0; r < KPT; r++) {
+                const int i = r * KS_DT + dtid;
+                if (i < S) {  // (whole warps: S and KS_DT are multiples of 32)
+                    const u64 o = stride >= 32 ? cand[i ^ stride] : __shfl_xor_sync(0xffffffffu, kk[r], stride);
+                    const bool lower = (i & stride) == 0, desc = ((i & size) == 0) || (size == S);
+                    kk[r] = ((kk[r] > o) == (lower == desc)) ? kk[r] : o;
+                }
+            }
+        }
+    }
+    ks_dsync();
+#pragma unroll
+    for (int r = 0; r < KPT; r++) {
+        const int i = r * KS_DT + dtid;
+        if (i < S) cand[i] = kk[r];
+    }
+    ks_dsync();
+}
+// Make room in a candidate buffer that is filling up: keep a superset of the best k of the evaluated keys cand[0, n) -- a
+// few sampling rounds, each of which drops the keys below a pivot that at least k keys beat -- and raise tau to the last
+// pivot, a valid LOWER bound of the k-th best.  No sort; the exact selection runs when the rounds do not free half of the
+// buffer, and once at the end of the row.  Returns the new n.
+static __device__ int ks_select(u64 *cand, int n, int k, u64 &tau, int *s_live, int *s_wsum, u64 *s_pivot, int dtid);
+static __device__ __noinline__ int ks_reduce(u64 *cand, int n, int k, u64 &tau, int *s_live, int *s_wsum, u64 *s_pivot, int dtid) {
+    for (int round = 0; round < 4; round++) {
+        const float qq = 65.f * (float)k / (float)max(n, 1);
+        const int j = (int)ceilf(qq + 3.f * sqrtf(qq) + 1.5f);
+        if (n <= 2 * k || n <= 192 || j > 40) break;
+        u64 pv = 0ull;
+        const int c = ks_pivot_round(cand, n, k, j, s_wsum, s_pivot, dtid, &pv);
+        if (c < 0) break;
+        n = c;
+        if (pv > tau) tau = pv;
+    }
+    if (n > KS_CAP / 2) n = ks_select(cand, n, k, tau, s_live, s_wsum, s_pivot, dtid);
+    return n;
+}
 // Exact selection among the evaluated keys cand[0, n) (0 = dead): leaves the best m = min(k, live) sorted best-first
 // in cand[0, m); returns m and, when m == k, sets tau to the k-th key.  (The reference's heap, s_plus.h:45-59.)
 // Sampling rounds shrink the set to a few hundred keys before the bitonic network; results never depend on the samples.
@@ -255,12 +341,23 @@ static __device__ int ks_select(u64 *cand, int n, int k, u64 &tau, int *s_live, 
         if (c < 0) break;
         n = c;
     }
+#if SPY_KS_REGSORT
+    int S = 256;
+    while (S < n) S <<= 1;
+    for (int i = n + dtid; i < S; i += KS_DT) cand[i] = 0ull;
+    if (dtid == 0) *s_live = 0;
+    ks_dsync();
+    if (S == 256) ks_sort_regs<256>(cand, dtid);
+    else if (S == 512) ks_sort_regs<512>(cand, dtid);
+    else ks_sort_regs<1024>(cand, dtid);
+#else
     int S = 32;
     while (S < n) S <<= 1;
     for (int i = n + dtid; i < S; i += KS_DT) cand[i] = 0ull;
     if (dtid == 0) *s_live = 0;
     ks_dsync();
     ks_bitonic_desc(cand, S, dtid);
+#endif
     for (int i = dtid; i < S; i += KS_DT)  // live keys are a prefix: find its end
         if (cand[i] != 0ull && (i == S - 1 || cand[i + 1] == 0ull)) *s_live = i + 1;
     ks_dsync();
@@ -765,7 +862,7 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
         bool hint_ok = false;
 #endif
         // exact values of the raw candidates (computeSimilarity, s_plus.h:129-156; threshold, s_plus.h:206)
-        auto evaluate = [&](int cnt) {
+        auto evaluate = [&](int cnt) __attribute__((always_inline)) {
             for (int i = n_eval + dtid; i < cnt; i += KS_DT) {
                 const u64 raw = cand[i];
                 const int col = (int)(unsigned)(raw & 0xffffffffull);
@@ -780,12 +877,16 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
             }
             n_eval = cnt;
         };
-        auto select_now = [&]() {  // evaluate what is buffered, keep the best k, raise tau
+        auto select_now = [&]() __attribute__((always_inline)) {  // evaluate what is buffered, keep the best k, raise tau
             ks_dsync();
             const int cnt = min(*reinterpret_cast<volatile int *>(&s_cnt), KS_CAP);
             evaluate(cnt);
             ks_dsync();
+#if SPY_KS_REDUCE
+            const int m = ks_reduce(cand, cnt, q.k, tau, &s_live, s_wsum, &s_pivot, dtid);
+#else
             const int m = ks_select(cand, cnt, q.k, tau, &s_live, s_wsum, &s_pivot, dtid);
+#endif
             lo = reject_bound(q, tau);
             n_eval = m;
             if (dtid == 0) { s_cnt = m; s_overflow = 0; }
@@ -822,7 +923,7 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
                 const int base = m.pn * q.W;
                 // One sweep over this warp's share of the snapshot.  lo_s: an extra (speculative) lower bound; sample: only ONE
                 // pseudo-randomly chosen tile, every touched slot of it (see the speculative bound below).
-                auto sweep = [&](float lo_s, bool sample) {
+                auto sweep = [&](float lo_s, bool sample) __attribute__((always_inline)) {
                 int gi = 0, i_res = 0, qn = 0;  // next group of four tiles of this warp's sweep, first tile of it still to do; queued quads
                 for (;;) {  // leaves the loop when the warp's share is done; re-entered after an overflow
                     bool overflow = false;
@@ -846,7 +947,7 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
                     }
                     const float lc = lo_u * (KIND == KIND_D ? fr.cD : fr.cC), la = lo_u * fr.A0;
                     // per-slot test of up to 32 queued quads, all lanes busy: one L2 round trip for the batch; false = buffer full
-                    auto batch = [&]() -> bool {
+                    auto batch = [&]() __attribute__((always_inline)) -> bool {
                         KS_T0(tb);
                         __syncwarp();
                         const int nb = min(qn, 32);
@@ -897,7 +998,7 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
                         return true;
                     };
                     // coarse test of one quad: false = no slot of it can enter the result
-                    auto quad_pass = [&](const float4 x) -> bool {
+                    auto quad_pass = [&](const float4 x) __attribute__((always_inline)) -> bool {
                         // (an untouched slot holds -0.0f: it fails x >= bound for every bound > 0)
                         bool pass = (x.x >= bound) | (x.y >= bound) | (x.z >= bound) | (x.w >= bound);
                         if (bound <= 0.f || !(KIND == KIND_RAW || KIND == KIND_C || KIND == KIND_D)) {
@@ -911,7 +1012,7 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
                         return pass;
                     };
                     // one tile: quads that cannot be rejected as a whole join the queue
-                    auto tile = [&](int T, const float4 x, const bool pass) {
+                    auto tile = [&](int T, const float4 x, const bool pass) __attribute__((always_inline)) {
                         const unsigned bal = __ballot_sync(0xffffffffu, pass);
                         if (pass) {
                             const int e = qn + __popc(bal & ((1u << lane) - 1u));
@@ -921,10 +1022,11 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
                         qn += __popc(bal);
                         KS_CNT(11, __popc(bal));
                     };
-                    while (!overflow && qn >= 32)  // (a round that follows an overflow starts with a full queue)
+                    while (!overflow && qn >= KS_QBATCH)  // (a round that follows an overflow starts with a full queue)
                         if (!batch()) overflow = true;
                     if (sample) {
-                        if (gi == 0) {  // tile (h % nGloc, (h >> 16) % 4) of this warp's share: spread over the panel, different per row
+                        // (at most 8 warps sample: 8 tiles of 128 slots never overflow the candidate buffer)
+                        if (gi == 0 && warp < KS_S_WARPS) {  // tile (h % nGloc, (h >> 16) % 4) of this warp's share: spread over the panel, different per row
                             unsigned h = (unsigned)m.t * 0x9E3779B1u + (unsigned)warp * 0x85EBCA6Bu;
                             h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12;
                             const int grp = dsub + DPQ * (int)(h % (unsigned)nGloc), i = (int)((h >> 16) & 3u);
@@ -933,8 +1035,8 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
                             const float4 x = i == 0 ? make_float4(xr[0], xr[1], xr[2], xr[3]) : i == 1 ? make_float4(xr[4], xr[5], xr[6], xr[7])
                                            : i == 2 ? make_float4(xr[8], xr[9], xr[10], xr[11]) : make_float4(xr[12], xr[13], xr[14], xr[15]);
                             tile(4 * grp + i, x, quad_pass(x));
-                            gi = 1;
                         }
+                        gi = 1;
                     } else
                     for (; gi < nGloc && !overflow; gi++) {
                         const int grp = dsub + DPQ * gi;
@@ -948,12 +1050,43 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
                         bool ps[4];
 #pragma unroll
                         for (int i = 0; i < 4; i++) ps[i] = quad_pass(make_float4(xr[4 * i], xr[4 * i + 1], xr[4 * i + 2], xr[4 * i + 3]));
+#if SPY_KS_VECQ
+                        // ... and queued at once when they fit: four votes, the queue positions of all passing quads from the votes
+                        // (four independent chains instead of four dependent tile steps)
+                        if (i_res == 0) {
+                            unsigned bal[4];
+#pragma unroll
+                            for (int i = 0; i < 4; i++) bal[i] = __ballot_sync(0xffffffffu, ps[i]);
+                            const int tot = __popc(bal[0]) + __popc(bal[1]) + __popc(bal[2]) + __popc(bal[3]);
+                            if (tot == 0) continue;
+                            if (qn + tot <= KS_QCAP) {
+                                const unsigned ltm = (1u << lane) - 1u;
+                                int off = qn;
+#pragma unroll
+                                for (int i = 0; i < 4; i++) {
+                                    if (ps[i]) {
+                                        const int e = off + __popc(bal[i] & ltm);
+                                        qx[e] = make_float4(xr[4 * i], xr[4 * i + 1], xr[4 * i + 2], xr[4 * i + 3]);
+                                        qc[e] = base + 512 * (4 * grp + i) + 128 * quarter + 4 * lane;
+                                    }
+                                    off += __popc(bal[i]);
+                                }
+                                qn = off;
+                                KS_CNT(11, tot);
+                                while (qn >= KS_QBATCH && !overflow)
+                                    if (!batch()) { overflow = true; i_res = 4; }  // (the group is consumed: resume behind it)
+                                if (overflow) break;
+                                continue;
+                            }
+                        }
+#else
                         if (i_res == 0 && !__any_sync(0xffffffffu, ps[0] | ps[1] | ps[2] | ps[3])) continue;
+#endif
 #pragma unroll
                         for (int i = 0; i < 4; i++) {
                             if (i >= i_res && !overflow) {
                                 tile(4 * grp + i, make_float4(xr[4 * i], xr[4 * i + 1], xr[4 * i + 2], xr[4 * i + 3]), ps[i]);
-                                if (qn >= 32 && !batch()) { overflow = true; i_res = i + 1; }
+                                if (qn >= KS_QBATCH && !batch()) { overflow = true; i_res = i + 1; }
                             }
                         }
                         if (overflow) break;
@@ -980,7 +1113,7 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
                 bool done = false;
                 KS_T0(tsp);
                 // sweep with the speculative bound tau_s, evaluate, count the buffered candidates that beat it (uniform)
-                auto try_bound = [&](u64 tau_s) -> int {
+                auto try_bound = [&](u64 tau_s) __attribute__((always_inline)) -> int {
                     sweep(reject_bound(q, tau_s), false);
                     const int c2 = min(*reinterpret_cast<volatile int *>(&s_cnt), KS_CAP);
                     evaluate(c2);
@@ -996,7 +1129,7 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
                     ks_dsync();
                     return above;
                 };
-                auto forget = [&]() {  // not validated: forget what was buffered; the valid bound is none again
+                auto forget = [&]() __attribute__((always_inline)) {  // not validated: forget what was buffered; the valid bound is none again
                     if (dtid == 0) s_cnt = 0;
                     n_eval = 0; tau = 0ull; lo = reject_bound(q, tau);
                     ks_dsync();
@@ -1026,7 +1159,7 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
                     evaluate(cnt);
                     ks_dsync();
                     const int width = min(q.W, q.n_cols - base);
-                    const float f = (float)(KS_D_WARPS * 128) / (float)max(width, 1), kf = (float)q.k * f;
+                    const float f = (float)(KS_S_WARPS * 128) / (float)max(width, 1), kf = (float)q.k * f;
 #ifdef SPY_SPEC_FORCE_RANK  // test builds: a bound that is almost never valid, to exercise the re-sweep
                     const int r_s = SPY_SPEC_FORCE_RANK;
 #else
@@ -1037,7 +1170,9 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
                     if (usable && ks_select(cand, cnt, r_s, tau_s, &s_live, s_wsum, &s_pivot, dtid) < r_s) tau_s = 0ull;
                     ks_dsync();
                     if (dtid == 0) s_cnt = 0;  // the sample was only read: its slots are all still in the snapshot
-                    n_eval = 0;
+                    // (and a bound that a full buffer forced during the sampling is forgotten with the keys it was taken from:
+                    // the k-th of them would be swept again and fail the strict test against itself)
+                    n_eval = 0; tau = 0ull; lo = reject_bound(q, tau);
                     ks_dsync();
                     if (tau_s != 0ull) {
                         done = try_bound(tau_s) >= q.k;
@@ -1109,16 +1244,20 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
 
 typedef void (*knn_stream_kernel_t)(const KnnStreamDev);
 
+}  // inline namespace
 }  // namespace spy
 
-// ---- host side (knn_stream.cu), used by the planner / launcher in knn_kernel.cu ------------------------------
+// ---- host side (knn_stream.cu, knn_stream_sparse.cu), used by the planner / launcher in knn_kernel.cu -----------
 namespace spy {
 struct StreamPlan {
-    int W, n_panels, cap;
+    int W, n_panels, cap, drain_warps;
     size_t smem_bytes;
 };
-// false when the stream engine does not cover the configuration (k too large for its candidate buffer)
-bool stream_plan(int k, int n_cols, int panel_width, int max_smem_optin, StreamPlan &sp);
+// Drain warps of the two builds of the kernel (8 / 16 unless a development build overrides them).
+int stream_drain_warps(bool sparse);
+// false when the stream engine does not cover the configuration (k too large for its candidate buffer).
+// drain_warps selects the build; sp.drain_warps returns it.
+bool stream_plan(int k, int n_cols, int panel_width, int max_smem_optin, int drain_warps, StreamPlan &sp);
 int64_t stream_scratch_bytes(int n_panels);
 int stream_launch(const spy_knn_args &a, const StreamPlan &sp, int kind, int exact_only, int grid, void *scratch,
                   int64_t scratch_bytes, cudaStream_t st);

@@ -31,17 +31,22 @@ def pytest_collection_modifyitems(config, items):
 
 
 # ---- both kernel generations: modules that list the `spy_engine` fixture run every test with the flat engine and with
-#      the stream engine preferred (configurations the stream engine does not cover fall back to the flat one) ----
+#      the stream engine preferred, in both of its builds (8 and 16 drain warps); configurations the stream engine does
+#      not cover fall back to the flat one ----
 def pytest_generate_tests(metafunc):
     if "spy_engine" in metafunc.fixturenames:
-        metafunc.parametrize("spy_engine", ["flat", "stream"], indirect=True)
+        metafunc.parametrize("spy_engine", ["flat", "stream8", "stream16"], indirect=True)
 
 
 @pytest.fixture
 def spy_engine(request):
     from similaripy_b200 import _engine
     saved = dict(_engine.DEFAULT_TUNING)
-    _engine.DEFAULT_TUNING["engine_prefer"] = request.param
+    if request.param == "flat":
+        _engine.DEFAULT_TUNING["engine_prefer"] = "flat"
+    else:
+        _engine.DEFAULT_TUNING["engine_prefer"] = "stream"
+        _engine.DEFAULT_TUNING["drain_warps"] = int(request.param[len("stream"):])
     yield request.param
     _engine.DEFAULT_TUNING.clear()
     _engine.DEFAULT_TUNING.update(saved)

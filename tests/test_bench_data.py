@@ -48,11 +48,20 @@ def test_engine_resolution_in_the_planner():
         assert rc == _lib.ERR_UNSUPPORTED, kw
         rc, a = plan(**kw)  # ... and takes the flat engine on its own
         assert rc == 0 and a.engine == _lib.ENGINE_FLAT, kw
-    # short rows stay on the flat engine when the planner knows the operand sizes (configs[4]: 200 x 100 products per row)
+    # the build of the stream kernel follows the products per (row, panel) when the planner knows the operand sizes:
+    # configs[4] (200 x 100 products per row, 5 panels) takes 16 drain warps, configs[1] (2e5 products per row) 8
     rc, a = plan(a_rows=5_000_000, a_nnz=1_000_000_000, b_rows=200_000, b_nnz=20_000_000)
-    assert rc == 0 and a.engine == _lib.ENGINE_FLAT
-    rc, a = plan(a_rows=200_000, a_nnz=200_000_000, b_rows=1_000_000, b_nnz=200_000_000)  # configs[1]: 2e5 products per row
-    assert rc == 0 and a.engine == _lib.ENGINE_STREAM
+    assert rc == 0 and a.engine == _lib.ENGINE_STREAM and a.group == 16
+    rc, a = plan(a_rows=200_000, a_nnz=200_000_000, b_rows=1_000_000, b_nnz=200_000_000)
+    assert rc == 0 and a.engine == _lib.ENGINE_STREAM and a.group == 8
+    w8 = a.panel_width
+    # ... an explicit request wins, and a plan that is fed back (engine and group as returned) resolves to itself
+    rc, a = plan(engine=_lib.ENGINE_STREAM, group=16, a_rows=200_000, a_nnz=200_000_000, b_rows=1_000_000, b_nnz=200_000_000)
+    assert rc == 0 and a.group == 16 and a.panel_width == w8  # (both builds hold a 40960-column panel)
+    rc, a = plan(engine=_lib.ENGINE_STREAM, group=8, a_rows=5_000_000, a_nnz=1_000_000_000, b_rows=200_000, b_nnz=20_000_000)
+    assert rc == 0 and a.group == 8
+    rc, a = plan(group=16)  # the flat engine's lanes per segment do not select a build when the engine is not asked for
+    assert rc == 0 and (a.engine == _lib.ENGINE_FLAT or a.group in (8, 16))
     rc, _ = plan(engine=7)
     assert rc < 0
     rc, _ = plan(threads=768)  # experiment builds only
