@@ -519,7 +519,11 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
             }
         };
         auto stage_queue_blocks = [&](const KsPass &d, int buf) {  // the queue warp's share, start to end
-            for (int b0 = KS_A_WARPS; b0 < 32; b0 += 3) {
+            // blocks behind the pass's last entry: their (zero) totals with one store -- a short target row leaves most of the
+            // queue warp's blocks empty, and scanning them one by one made it the last warp at the end-of-pass barrier
+            const int nb = (d.n + 31) >> 5;
+            if (lane >= max(nb, KS_A_WARPS)) stage0[buf * KS_STAGE_WORDS + 3 * KS_CH + lane] = 0u;
+            for (int b0 = KS_A_WARPS; b0 < nb; b0 += 3) {
                 uint2 se[3];
                 float v[3];
 #pragma unroll

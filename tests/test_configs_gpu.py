@@ -78,6 +78,51 @@ def _check_rows(job, rows, k, what, rtol=1e-5):
             assert set(rc[rv > band * (1 + 10 * rtol)].tolist()) <= set(gc.tolist()), f"{what}: row {targets[i]} columns"
 
 
+def _oracle_rows(job, picks, k, what, rtol=1e-5):
+    """Rows `picks` of the job against the ORACLE's kernel (oracle/spy_oracle.c, the restatement of s_plus.h:265-453 that is
+    pinned against the compiled reference) on the job's own operands: A cut to the picked target rows, B to the rows those
+    reference (every other row empty), the row / column vectors as the device pre-processing left them."""
+    import torch
+    import scipy.sparse as sp
+    from oracle import oracle
+    from parity import assert_topk_parity
+    torch.cuda.synchronize()
+    A, B, P, v = job.A, job.B, job.params, job.vectors
+    targets = job.targets.cpu().numpy()
+    ts = [int(targets[i]) for i in picks]
+    aip = A.indptr.cpu().numpy().astype(np.int64)
+    a_parts = [(A.indices[aip[t]:aip[t + 1]].cpu().numpy(), A.data[aip[t]:aip[t + 1]].cpu().numpy()) for t in ts]
+    a_indptr = np.concatenate([[0], np.cumsum([len(x[0]) for x in a_parts])]).astype(np.int32)
+    a_indices = np.concatenate([x[0] for x in a_parts]).astype(np.int32)
+    a_data = np.concatenate([x[1] for x in a_parts]).astype(np.float32)
+    used = torch.unique(torch.from_numpy(a_indices).to(B.indptr.device).long())
+    starts, ends = B.indptr[used].long(), B.indptr[used + 1].long()
+    lens = ends - starts
+    pos = torch.arange(int(lens.sum()), device=used.device) - torch.repeat_interleave(torch.cumsum(lens, 0) - lens, lens)
+    q = torch.repeat_interleave(starts, lens) + pos
+    b_len = np.zeros(B.n_rows, dtype=np.int64)
+    b_len[used.cpu().numpy()] = lens.cpu().numpy()
+    b_indptr = np.concatenate([[0], np.cumsum(b_len)]).astype(np.int32)
+    b = (B.data[q].cpu().numpy().astype(np.float32), B.indices[q].cpu().numpy().astype(np.int32), b_indptr)
+    e = np.array([], dtype=np.float32)
+    row_vec = lambda n: v[n][torch.tensor(ts, device=v[n].device)].cpu().numpy().astype(np.float32) if v.get(n) is not None else e
+    col_vec = lambda n: v[n].cpu().numpy().astype(np.float32) if v.get(n) is not None else e
+    zi = np.zeros(1, dtype=np.int32)
+    rows, cols, vals = oracle.knn_kernel(
+        np.arange(len(ts), dtype=np.int32), (a_data, a_indices, a_indptr), b,
+        row_vec("Xt"), col_vec("Yt"), row_vec("Xc"), col_vec("Yc"), row_vec("Xd"), col_vec("Yd"),
+        P["a1"], P["l1"], P["l2"], P["l3"], P["t1"], P["t2"], P["stabilized_shrink"], P["bayesian_shrink"], P["threshold"],
+        k, job.n_cols, 0, zi, zi, 0, zi, zi)
+    ref = oracle.slab_to_csr(rows, cols, vals, len(ts), job.n_cols)
+    gc = job.out_cols.cpu().numpy().reshape(-1, k)[picks]
+    gv = job.out_vals.cpu().numpy().reshape(-1, k)[picks]
+    gn = job.out_counts.cpu().numpy()[picks]
+    rr = np.concatenate([np.full(int(n), i) for i, n in enumerate(gn)])
+    keep = np.concatenate([np.arange(k) < n for n in gn])
+    got = sp.csr_array((gv.ravel()[keep], (rr, gc.ravel()[keep])), shape=(len(ts), job.n_cols))
+    assert_topk_parity(ref, got, k=k, rtol=rtol, what=f"{what} oracle kernel rows")
+
+
 def _job(matrix1, matrix2, k, target_rows, tuning=None, **kw):
     from similaripy_b200 import _engine
     job = _engine.prepare_job(matrix1, matrix2, k=k, target_rows=target_rows, verbose=False, device=0, tuning=tuning, **kw)
@@ -127,6 +172,7 @@ def test_cfg3_s_plus_full_matrix_size():
     assert int(job.args.n_panels) >= 9
     assert job.out_counts.cpu().numpy().min() == k
     _check_rows(job, [0, 299, 599], k, "cfg3")
+    _oracle_rows(job, [1, 300, 598], k, "cfg3")
     # a different launch plan (2 CTAs per SM, narrower panels, other group width) selects the same neighbours
     job2 = _job(x, None, k, rows, tuning=dict(threads=512, panel_width=12_800, group=8), **kw)
     a = job.out_vals.view(-1, k)
@@ -151,6 +197,7 @@ def test_cfg4_rp3beta_full_matrix_size():
     job = _job(m1n, m2n, k, rows, weight_depop_matrix2=pop, p2=0.6, l3=1.0)
     assert job.out_counts.cpu().numpy().min() == k
     _check_rows(job, [0, 300, 599], k, "cfg4")
+    _oracle_rows(job, [2, 301, 597], k, "cfg4")
     # and the public entry point gives the same rows
     res = sim.rp3beta(urm.T, alpha=1.0, beta=0.6, k=k, target_rows=rows, verbose=False, on_device=True)
     host = sim.to_host(res)
@@ -182,6 +229,7 @@ def test_cfg5_recommend_with_filter_full_matrix_size():
     # unfiltered kernel rows against the float64 restatement, then the filter removes exactly the seen items
     job = _job(urm, s_t, k, rows)
     _check_rows(job, [0, 999, 1999], k, "cfg5")
+    _oracle_rows(job, [1, 1000, 1998], k, "cfg5")
     for i in (0, 999, 1999):
         r = int(rows[i])
         rc, rv = _row_reference(job, r, 20_000)
