@@ -315,40 +315,69 @@ def job_products(job):
     return int((cum[hi] - cum[lo]).sum().item()), int((hi - lo).sum().item())
 
 
-def kernel_line(name, job, n_rows_total, peak, reps=3):
-    """Hot-kernel numbers of one prepared job (tables built, operands resident): median of `reps` launches."""
+def kernel_line(name, job, n_rows_total, peak, reps=3, world=1):
+    """Hot-kernel numbers of one prepared job (tables built, operands resident): median of `reps` launches.  world > 1: the
+    job was prepared under sharded.shard_rows(gather=True) -- this rank holds its share of the sampled target rows; the time
+    is the maximum over the ranks, plus ONE NCCL all-gather of the output slab (timed once, after the launches)."""
     import torch
     products, nnz_a = job_products(job)
+    n_t = job.n_targets
     ms = []
     for _ in range(reps + 1):
+        if world > 1:
+            torch.distributed.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(job.ctx.stream); job.run(); e1.record(job.ctx.stream); torch.cuda.synchronize()
         ms.append(e0.elapsed_time(e1))
     k_ms = float(np.median(ms[1:]))
     out_nnz = int(job.out_counts.sum().item())
-    alg = 8 * job.n_targets + 16 * nnz_a + 8 * products + 8 * out_nnz
-    return {"config": name, "target_rows_sampled": job.n_targets, "target_rows_total": n_rows_total, "k": job.k,
-            "rows_per_s": round(job.n_targets / k_ms * 1e3, 1), "out_nnz_per_s": round(out_nnz / k_ms * 1e3, 1),
+    gather_ms = None
+    if world > 1:
+        torch.distributed.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        job.gather()
+        torch.cuda.synchronize()
+        gather_ms = (time.perf_counter() - t0) * 1e3
+        mx = torch.tensor([k_ms, gather_ms], device=job.out_cols.device, dtype=torch.float64)
+        sm = torch.tensor([products, nnz_a, out_nnz, n_t], device=job.out_cols.device, dtype=torch.float64)
+        torch.distributed.all_reduce(mx, op=torch.distributed.ReduceOp.MAX)
+        torch.distributed.all_reduce(sm, op=torch.distributed.ReduceOp.SUM)
+        k_ms, gather_ms = float(mx[0]), float(mx[1])
+        products, nnz_a, out_nnz, n_t = (int(x) for x in sm.tolist())
+    alg = 8 * n_t + 16 * nnz_a + 8 * products + 8 * out_nnz
+    step_ms = k_ms + (gather_ms or 0.0)
+    line = {"config": name, "target_rows_sampled": n_t, "target_rows_total": n_rows_total, "k": job.k,
+            "rows_per_s": round(n_t / step_ms * 1e3, 1), "out_nnz_per_s": round(out_nnz / step_ms * 1e3, 1),
             "kernel_ms": round(k_ms, 3), "products": products, "gproducts_per_s": round(products / k_ms / 1e6, 1),
-            "roofline": {"bound": "hbm", "achieved": round(alg / k_ms / 1e6, 1), "peak": peak, "unit": "GB/s",
-                         "frac": round(alg / k_ms / 1e6 / peak, 4), "algorithmic_bytes": alg},
-            "full_job_estimate_s": round(n_rows_total / (job.n_targets / k_ms * 1e3), 2),
+            "roofline": {"bound": "hbm", "achieved": round(alg / k_ms / 1e6, 1), "peak": peak * world, "unit": "GB/s",
+                         "frac": round(alg / k_ms / 1e6 / (peak * world), 4), "algorithmic_bytes": alg},
+            "full_job_estimate_s": round(n_rows_total / (n_t / step_ms * 1e3), 2),
             "plan": {"engine": int(job.args.engine), "n_panels": int(job.args.n_panels),
                      "panel_width": int(job.args.panel_width), "group": int(job.args.group)},
-            "sample": f"hot kernel on {job.n_targets} seeded random target rows of {n_rows_total}; operands at full size",
+            "sample": f"hot kernel on {n_t} seeded random target rows of {n_rows_total}; operands at full size",
             "cpu_baseline": None}
+    if world > 1:
+        line["n_gpus"] = world
+        line["all_gather_ms"] = round(gather_ms, 3)
+        line["sample"] += (f"; ONE call's target rows cut by work over {world} GPUs, kernel time = max over the ranks, rows/s "
+                           "includes one NCCL all-gather of the output slab")
+    return line
 
 
 def sample_rows(n, m, seed):
     return np.sort(np.random.default_rng(seed).choice(n, size=min(m, n), replace=False)).astype(np.int32)
 
 
-def other_configs(local, peak, scale):
-    """BASELINE.json configs[2..4] on one GPU: full-size synthetic operands, a seeded sample of the target rows."""
+def other_configs(local, peak, scale, world=1):
+    """BASELINE.json configs[2..4]: full-size synthetic operands, a seeded sample of the target rows; on one GPU, or (world > 1)
+    the sample cut by work over the ranks like any sharded call."""
     import torch
     import similaripy_b200 as sim
-    from similaripy_b200 import _engine
+    from similaripy_b200 import _engine, sharded
+    import contextlib
     dev = torch.device("cuda", local)
+    shard = (lambda: sharded.shard_rows(gather=True)) if world > 1 else contextlib.nullcontext
     sc = lambda n: max(64, int(n * scale))
     out = []
 
@@ -361,24 +390,27 @@ def other_configs(local, peak, scale):
 
     def cfg2():  # s_plus(X, k=200, shrink=10), public defaults l1=l2=0.5, t1=t2=1, c1=c2=0.5 (similarity.py:509-515)
         x = device_matrix(sc(500_000), sc(500_000), 2e-3, 3, dev)
-        job = _engine.prepare_job(x, None, k=200, target_rows=sample_rows(sc(500_000), 20_000, 3), verbose=False, device=local,
-                                  l1=0.5, l2=0.5, t1=1.0, t2=1.0, c1=0.5, c2=0.5, stabilized_shrink=10.0)
-        return kernel_line("configs[2]: s_plus k=200 shrink=10, 500k x 500k d=2e-3", job, sc(500_000), peak)
+        with shard():
+            job = _engine.prepare_job(x, None, k=200, target_rows=sample_rows(sc(500_000), 20_000, 3), verbose=False, device=local,
+                                      l1=0.5, l2=0.5, t1=1.0, t2=1.0, c1=0.5, c2=0.5, stabilized_shrink=10.0)
+        return kernel_line("configs[2]: s_plus k=200 shrink=10, 500k x 500k d=2e-3", job, sc(500_000), peak, world=world)
 
     def cfg3():  # rp3beta(URM.T, alpha=1, beta=0.6, k=100): item-item (benchmark.py:161), similarity.py:477-503
         urm = device_matrix(sc(2_000_000), sc(500_000), 5e-4, 4, dev)
         pop = _engine.axis_sum(urm, 0)
-        job = _engine.prepare_job(sim.normalize(urm.T, norm="l1", axis=1), sim.normalize(urm, norm="l1", axis=1), k=100,
-                                  target_rows=sample_rows(sc(500_000), 60_000, 4), verbose=False, device=local,
-                                  weight_depop_matrix2=pop, p2=0.6, l3=1.0)
-        return kernel_line("configs[3]: rp3beta beta=0.6 k=100 item-item, URM 2M x 500k d=5e-4", job, sc(500_000), peak)
+        with shard():
+            job = _engine.prepare_job(sim.normalize(urm.T, norm="l1", axis=1), sim.normalize(urm, norm="l1", axis=1), k=100,
+                                      target_rows=sample_rows(sc(500_000), 60_000, 4), verbose=False, device=local,
+                                      weight_depop_matrix2=pop, p2=0.6, l3=1.0)
+        return kernel_line("configs[3]: rp3beta beta=0.6 k=100 item-item, URM 2M x 500k d=5e-4", job, sc(500_000), peak, world=world)
 
     def cfg4():  # dot_product(URM, S.T, k=100, filter_cols=URM): S with ~100 neighbours per item
         urm = device_matrix(sc(5_000_000), sc(200_000), 1e-3, 5, dev)
         s_t = device_matrix(sc(200_000), sc(200_000), 5e-4, 55, dev)
-        job = _engine.prepare_job(urm, s_t, k=100, target_rows=sample_rows(sc(5_000_000), 500_000, 5), filter_cols=urm,
-                                  verbose=False, device=local)
-        return kernel_line("configs[4]: dot_product URM x S.T filter_cols=URM k=100, URM 5M x 200k d=1e-3", job, sc(5_000_000), peak)
+        with shard():
+            job = _engine.prepare_job(urm, s_t, k=100, target_rows=sample_rows(sc(5_000_000), 500_000, 5), filter_cols=urm,
+                                      verbose=False, device=local)
+        return kernel_line("configs[4]: dot_product URM x S.T filter_cols=URM k=100, URM 5M x 200k d=1e-3", job, sc(5_000_000), peak, world=world)
 
     guarded("configs[2]", cfg2)
     guarded("configs[3]", cfg3)
@@ -586,10 +618,10 @@ def run_ours(args):
         del urm_host, h
 
     configs = None
-    if rank == 0 and world == 1 and not args.no_extras:
+    if not args.no_extras:  # (every rank takes part when world > 1: the sampled target rows are cut over the ranks)
         del urm, urm_raw, m1
         torch.cuda.empty_cache()
-        configs = other_configs(local, peak, args.scale)
+        configs = other_configs(local, peak, args.scale, world)
 
     if rank == 0:
         line = {
