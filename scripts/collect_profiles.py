@@ -31,7 +31,7 @@ for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
 setup = ("sequential_mean", "bm25_apply", "doclen_df", "idf_kernel", "at_cuda", "native::", "cuda::", "at::", "cub::", "sort_rows")
 step = {k: v for k, v in agg.items() if "spy::" in k and not any(x in k for x in setup)}
 step_tot = sum(v[1] for v in step.values())
-hot = sum(v[1] for k, v in step.items() if "knn_flat_kernel" in k)
+hot = sum(v[1] for k, v in step.items() if "knn_flat_kernel" in k or "knn_stream_kernel" in k)
 out.append("")
 out.append(f"kernels of the timed step only (without data generation and bm25): hot kernel {100 * hot / step_tot:.1f} % of {step_tot / 1e6:.1f} ms "
            f"-- bench.py reports kernel_share_of_step = {json.load(open(os.path.join(src, f'bench_{tag}.json')))['roofline']['kernel_share_of_step']}")
@@ -49,7 +49,7 @@ for line in summ.splitlines():
     if line.startswith("dram__bytes_read.sum"): rd = float(line.split()[1]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Tbyte": 1e12}[line.split()[2]]
     if line.startswith("dram__bytes_write.sum"): wr = float(line.split()[1]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Tbyte": 1e12}[line.split()[2]]
 if rd is not None and wr is not None:
-    json.dump({"kernel": f"knn_flat_kernel {tag}", "workload_nnz": bench["config"]["nnz"], "dram_bytes_per_launch": int(rd + wr),
+    json.dump({"kernel": f"{r.get('kernel', 'knn_stream_kernel')} {tag}", "workload_nnz": bench["config"]["nnz"], "dram_bytes_per_launch": int(rd + wr),
                "source": f"profiles/{rnd}/knn_{tag}_ncu_summary.txt (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)"},
               open(os.path.join(ROOT, "profiles", "knn_traffic.json"), "w"), indent=1)
 print("\n".join(out[:8])); print(summ[:1500])

@@ -16,5 +16,8 @@ fi
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv \
     python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu > gpurun_out/ncu_launches_$TAG.log 2>&1; echo "ncu list rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:knn_ -c 1 -o gpurun_out/prof_knn_$TAG -f \
-    python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu > gpurun_out/ncu_full_$TAG.log 2>&1; echo "ncu full rc=$?"
+    python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu --no-extras > gpurun_out/ncu_full_$TAG.log 2>&1; echo "ncu full rc=$?"
+# DRAM traffic of the hot kernel on the other configurations (configs[4]: B is L2 resident): one launch each
+timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,lts__t_sector_hit_rate.pct --clock-control none -k regex:knn_stream --csv \
+    --log-file gpurun_out/configs_traffic_$TAG.csv python scripts/bench_configs.py cfg3 cfg4 cfg5 > gpurun_out/configs_traffic_$TAG.log 2>&1; echo "ncu configs rc=$?"
 ls -la gpurun_out | tail -20

@@ -138,10 +138,20 @@ __device__ __forceinline__ void ks_mbar_init(unsigned bar, unsigned count) {
 __device__ __forceinline__ void ks_mbar_arrive(unsigned bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// (suspend-time hint: the waiting thread sleeps in the barrier unit until the phase completes or ~20 us pass, instead of
+// spinning through the loop below -- the spinning lanes of the idle side took 7 % of all issued instructions, ncu r02v3)
+#ifndef SPY_KS_WAIT_HINT
+#define SPY_KS_WAIT_HINT 20000
+#endif
 __device__ __forceinline__ bool ks_mbar_try(unsigned bar, unsigned parity) {
     unsigned ok;
+#if SPY_KS_WAIT_HINT
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(bar), "r"(parity), "r"((unsigned)SPY_KS_WAIT_HINT) : "memory");
+#else
     asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+#endif
     return ok != 0;
 }
 // bounded wait (about two seconds): a protocol bug must end in an error, not in a hung device
