@@ -104,7 +104,7 @@ static int choose_engine(const spy_knn_args &a, int max_smem_optin, StreamPlan &
         if (a.a_nnz > 0 && a.b_nnz > 0 && a.a_rows > 0 && a.b_rows > 0) {
             const int panels_est = std::max(1, (std::max(a.n_cols, 1) + 40959) / 40960);
             const double per_panel = ((double)a.a_nnz / a.a_rows) * ((double)a.b_nnz / a.b_rows) / panels_est;
-            if (per_panel < 8192.0) drain = stream_drain_warps(true);
+            if (per_panel < 5120.0) drain = stream_drain_warps(true);  // (its touched lists hold 6144 slots per panel)
         }
     }
     const bool eligible = !exact_only && a.target_mode != SPY_SEL_MATRIX && (a.threads == 0 || a.threads == 1024) &&

@@ -96,7 +96,19 @@ constexpr int KS_A_WARPS = KS_X_WARPS - 1;     // warps D+1..31 expand
 constexpr int KS_X_THREADS = KS_X_WARPS * 32;
 constexpr int KS_DT = KS_D_WARPS * 32;
 constexpr int KS_U = SPY_KS_U;                 // 16-byte chunks per lane per batch (ring: 16 * KS_U bytes per lane)
-constexpr int KS_CH = 1024;                    // entries of a target row per pass (32 blocks of 32)
+#ifndef SPY_KS_SPARSE
+#define SPY_KS_SPARSE (SPY_KS_D_WARPS == 16)   // touched-list hand-over of sparse panels (the 16-drain-warp build)
+#endif
+// Sparse panels (SPY_KS_SPARSE): the expansion lists the slots it touches for the first time; a panel with at most
+// KS_LIST_CAP touched slots is handed over as (column, sum) pairs -- KS_SP_J pairs per expansion-side thread, in the TMEM
+// lane of that thread -- instead of as a 160 KB snapshot that the drain has to sweep.
+constexpr int KS_CH = SPY_KS_SPARSE ? 512 : 1024;  // entries of a target row per pass (blocks of 32; the list takes the room)
+constexpr int KS_LIST_CAP = SPY_KS_SPARSE ? 6144 : 0;
+constexpr int KS_SP_J = (KS_LIST_CAP + KS_X_THREADS - 1) / KS_X_THREADS;  // pairs per thread
+constexpr int KS_SP_COLS = 2 * KS_SP_J;                                    // TMEM columns per (lane quarter, sub-group of warps)
+static_assert(!SPY_KS_SPARSE || SPY_KS_LOCAL, "the list holds slot offsets");
+static_assert(!SPY_KS_SPARSE || (KS_X_WARPS == KS_D_WARPS && KS_A_WARPS <= KS_CH / 32 && 4 * KS_SP_COLS <= 512 && KS_SP_J % 4 == 0),
+              "sparse hand-over: drain warp (quarter, sub) reads what expansion-side warp (quarter, sub) wrote");
 constexpr int KS_CAP = 1024;                   // candidate buffer (keys); k <= KS_CAP / 2
 constexpr int KS_S_WARPS = KS_D_WARPS < 8 ? KS_D_WARPS : 8;  // drain warps that take part in the sample of a first panel
 constexpr int KS_QBATCH = KS_D_WARPS > 8 ? 16 : 32;  // queued quads that trigger their per-slot test
@@ -116,13 +128,15 @@ struct KsQueue {  // cursor of the row queue (shared memory; lane 0 of the queue
 };
 struct KsMsg {    // what the expansion side hands to the drain with every snapshot (shared memory, double buffered)
     int t, i_out, pn, flags, landed;
+    int sparse_n;  // >= 0: the panel was handed over as that many (column, sum) pairs; -1: as a dense snapshot
 };
 
 __host__ __device__ constexpr size_t ks_ring_bytes() { return SPY_KS_RING ? (size_t)KS_A_WARPS * 32 * KS_U * 16 : 0; }
 __host__ __device__ constexpr size_t ks_stage_bytes() { return (size_t)2 * (3 * KS_CH * 4 + 32 * 4); }
 __host__ __device__ constexpr size_t ks_queue_bytes() { return (size_t)KS_D_WARPS * KS_QCAP * (16 + 4); }
 __host__ __device__ constexpr size_t ks_pad_bytes() { return SPY_KS_LOCAL ? 16 : 0; }  // the slot filler pairs are added to
-__host__ __device__ constexpr size_t ks_fixed_bytes() { return ks_pad_bytes() + ks_ring_bytes() + ks_stage_bytes() + ks_queue_bytes() + (size_t)KS_CAP * 8; }
+__host__ __device__ constexpr size_t ks_list_bytes() { return (size_t)KS_LIST_CAP * 2; }
+__host__ __device__ constexpr size_t ks_fixed_bytes() { return ks_pad_bytes() + ks_ring_bytes() + ks_stage_bytes() + ks_queue_bytes() + (size_t)KS_CAP * 8 + ks_list_bytes(); }
 
 // ---- PTX helpers --------------------------------------------------------------------------------------------
 __device__ __forceinline__ void ks_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
@@ -410,7 +424,9 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
     ptr += 2 * KS_STAGE_WORDS * 4;
     float4 *qx_all = reinterpret_cast<float4 *>(ptr); ptr += (size_t)KS_D_WARPS * KS_QCAP * 16;
     int *qc_all = reinterpret_cast<int *>(ptr); ptr += (size_t)KS_D_WARPS * KS_QCAP * 4;
-    u64 *cand = reinterpret_cast<u64 *>(ptr);
+    u64 *cand = reinterpret_cast<u64 *>(ptr); ptr += (size_t)KS_CAP * 8;
+    unsigned short *list = reinterpret_cast<unsigned short *>(ptr);  // SPY_KS_SPARSE: slots touched for the first time in this panel
+    (void)list;
 
     __shared__ __align__(8) unsigned long long s_full, s_empty;
     __shared__ __align__(8) u64 s_pivot;
@@ -419,6 +435,10 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
     __shared__ KsMsg s_msg[2];
     __shared__ unsigned s_tmem;
     __shared__ int s_cnt, s_overflow, s_live, s_wsum[KS_D_WARPS];
+    // entries of `list` (keeps counting past KS_LIST_CAP: the panel is then handed over densely); two counters, used by
+    // alternate hand-overs: the one a hand-over consumed is cleared behind that hand-over's last barrier, when every warp
+    // has read it, and is appended to again only after the NEXT hand-over
+    __shared__ int s_list_n[2];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 #if SPY_KS_TIMING
@@ -435,7 +455,10 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
         ks_mbar_init(full32, 1);
         ks_mbar_init(empty32, KS_D_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        s_cnt = 0; s_overflow = 0; s_live = 0;
+        s_cnt = 0; s_overflow = 0; s_live = 0; s_list_n[0] = 0; s_list_n[1] = 0;
+#if SPY_KS_LOCAL
+        acc[q.W] = 0.f;  // the spare slot filler pairs add 0 to: never "untouched"
+#endif
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"((unsigned)__cvta_generic_to_shared(&s_tmem)) : "memory");
@@ -662,14 +685,31 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
         // ---- snapshot bookkeeping (uniform over the warps of the side) ----
         unsigned seq = 0u;  // snapshots / messages posted so far
         bool panel_landed = false, m_landed = false;
-        auto post = [&](int t, int i_out, int pn, int flags, int landed) {  // one thread: message + "snapshot full"
+        auto post = [&](int t, int i_out, int pn, int flags, int landed, int sparse_n) {  // one thread: message + "snapshot full"
             KsMsg *m = &s_msg[seq & 1u];
-            m->t = t; m->i_out = i_out; m->pn = pn; m->flags = flags; m->landed = landed;
+            m->t = t; m->i_out = i_out; m->pn = pn; m->flags = flags; m->landed = landed; m->sparse_n = sparse_n;
             ks_mbar_arrive(full32);
         };
+#if SPY_KS_SPARSE
+        bool listing = true;  // this warp still appends first touches to the list of the open panel (uniform over the warp)
+        // a product into the open panel; true: it was the first one to reach its slot (the add returned the "untouched" mark)
+        auto add_first = [&](unsigned slot_off, float prod) __attribute__((always_inline)) -> bool {
+            float old;
+            asm volatile("atom.shared.add.f32 %0, [%1], %2;" : "=f"(old) : "r"(accl + slot_off), "f"(prod) : "memory");
+            return __float_as_uint(old) == kSentinelBits;
+        };
+#endif
         auto snapshot = [&](const KsPass &dp) {  // dp: the pass that completed the panel
             KS_T0(ts);
             const int m_t = dp.t, m_pn = dp.pn;
+#if SPY_KS_SPARSE
+            // (all appends of the panel are behind the end-of-pass barrier; nobody appends again before this function's last barrier)
+            const int n_list = *reinterpret_cast<volatile int *>(&s_list_n[seq & 1u]);
+            const bool sparse = n_list <= KS_LIST_CAP;
+#else
+            const int n_list = -1;
+            const bool sparse = false;
+#endif
             // the drain must have released the previous snapshot (and read its message)
             if (lane == 0) ks_mbar_wait(empty32, (seq & 1u) ^ 1u, p.err, 2);
             __syncwarp();
@@ -687,6 +727,32 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
                     ks_bar_sync(3, KS_X_THREADS);
                 }
                 const int sub = wx >> 2;  // the warps of one lane quarter take every (KS_X_WARPS / 4)-th tile
+#if SPY_KS_SPARSE
+                if (sparse) {  // the listed slots only: (column, sum) pairs into this thread's TMEM lane, the slots reset
+                    const int nj = (n_list + KS_X_THREADS - 1) / KS_X_THREADS;
+                    for (int j0 = 0; j0 < nj; j0 += 4) {  // four rounds at a time: independent chains, one tcgen05.st
+                        unsigned col[4], sl[4];
+                        float x[4];
+#pragma unroll
+                        for (int r = 0; r < 4; r++) {
+                            const int i = (j0 + r) * KS_X_THREADS + (tid - KS_DT);
+                            sl[r] = i < n_list ? (unsigned)list[i] : 0xffffffffu;
+                        }
+#pragma unroll
+                        for (int r = 0; r < 4; r++) {
+                            col[r] = 0xffffffffu; x[r] = sentinel;
+                            if (sl[r] != 0xffffffffu) { x[r] = acc[sl[r]]; col[r] = (unsigned)base + sl[r]; }
+                        }
+#pragma unroll
+                        for (int r = 0; r < 4; r++)
+                            if (sl[r] != 0xffffffffu) acc[sl[r]] = sentinel;
+                        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                                     ::"r"(tmem_q + (unsigned)(sub * KS_SP_COLS + 2 * j0)), "r"(col[0]), "r"(__float_as_uint(x[0])),
+                                     "r"(col[1]), "r"(__float_as_uint(x[1])), "r"(col[2]), "r"(__float_as_uint(x[2])), "r"(col[3]),
+                                     "r"(__float_as_uint(x[3])) : "memory");
+                    }
+                } else
+#endif
                 for (int T = sub; T < nT; T += KS_X_WARPS / 4) {
                     const unsigned a = acc32 + (unsigned)(512 * T + 128 * (warp & 3) + 4 * lane) * 4u;
                     const float4 x = lds128(a);
@@ -697,7 +763,15 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
             }
             ks_tc_fence_before();
             ks_bar_sync(2, KS_X_THREADS);  // every slot of the panel is in TMEM and reset
-            if (tid == KS_DT) post(dp.t, dp.i_out, dp.pn, dp.flags, m_landed ? 1 : 0);
+            if (tid == KS_DT) {
+#if SPY_KS_SPARSE
+                s_list_n[seq & 1u] = 0;
+#endif
+                post(dp.t, dp.i_out, dp.pn, dp.flags, m_landed ? 1 : 0, sparse ? n_list : -1);
+            }
+#if SPY_KS_SPARSE
+            listing = true;
+#endif
             seq++;
             KS_ACC(3, ts);
         };
@@ -799,6 +873,11 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
                 const unsigned lc = lp;
                 const bool more = f < F1;
                 if (more) issue();
+#if SPY_KS_SPARSE
+                bool first[2 * KS_U];
+#pragma unroll
+                for (int r = 0; r < 2 * KS_U; r++) first[r] = false;
+#endif
 #pragma unroll
                 for (int r = 0; r < KS_U; r++) {
                     if (lc & (1u << r)) {
@@ -807,8 +886,13 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
 #ifdef SPY_KS_NOADDS  // timing experiment: gathers only (results are wrong)
                         if (pr[r].x + pr[r].z == 0x12345u) smem_add_f32(accl, vc[r]);
 #else
+#if SPY_KS_SPARSE
+                        first[2 * r] = add_first(pr[r].x, __fmul_rn(__uint_as_float(pr[r].y), vc[r]));
+                        first[2 * r + 1] = add_first(pr[r].z, __fmul_rn(__uint_as_float(pr[r].w), vc[r]));
+#else
                         smem_add_f32(accl + pr[r].x, __fmul_rn(__uint_as_float(pr[r].y), vc[r]));
                         smem_add_f32(accl + pr[r].z, __fmul_rn(__uint_as_float(pr[r].w), vc[r]));
+#endif
 #endif
 #else
                         const unsigned d0 = pr[r].x - base, d1 = pr[r].z - base;
@@ -821,6 +905,28 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
 #endif
                     }
                 }
+#if SPY_KS_SPARSE
+                // the slots this batch touched for the first time join the panel's list: one reservation per warp and batch
+                if (listing) {
+                    unsigned fb_[2 * KS_U];
+                    int nf = 0;
+#pragma unroll
+                    for (int r = 0; r < 2 * KS_U; r++) { fb_[r] = __ballot_sync(0xffffffffu, first[r]); nf += __popc(fb_[r]); }
+                    if (nf != 0) {
+                        int at = 0;
+                        if (lane == 0) at = atomicAdd(&s_list_n[seq & 1u], nf);
+                        at = __shfl_sync(0xffffffffu, at, 0);
+                        if (at + nf > KS_LIST_CAP) listing = false;  // (the count alone tells the hand-over that the list is incomplete)
+                        else {
+#pragma unroll
+                            for (int r = 0; r < 2 * KS_U; r++) {
+                                if (first[r]) list[at + __popc(fb_[r] & ((1u << lane) - 1u))] = (unsigned short)(((r & 1) ? pr[r >> 1].z : pr[r >> 1].x) >> 2);
+                                at += __popc(fb_[r]);
+                            }
+                        }
+                    }
+                }
+#endif
                 have = more;
             }
             KS_ACC(1, tp);
@@ -841,7 +947,7 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
         // no more rows: tell the drain
         if (tid == KS_DT) {
             ks_mbar_wait(empty32, (seq & 1u) ^ 1u, p.err, 3);
-            post(0, 0, 0, KS_FLAG_STOP, 0);
+            post(0, 0, 0, KS_FLAG_STOP, 0, -1);
         }
 #if SPY_KS_TIMING
         // [0] snapshot  [1] pass body  [2] end-of-pass barrier  [3] snapshot (again)  [4] wait for the drain  [5] pass setup + first issue
@@ -943,6 +1049,57 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
                     bool overflow = false;
                     const float lo_u = fmaxf(lo, lo_s);  // (lo itself rises when a full buffer forces a selection)
                     const bool flt = filter && !sample;
+#if SPY_KS_SPARSE
+                    if (m.sparse_n >= 0) {
+                        // The panel came as (column, sum) pairs, KS_X_THREADS per round `gi`, one per TMEM lane: every pair is
+                        // tested per slot (its Y values are gathered; there is no lane-wise bound for arbitrary columns) and
+                        // the survivors are buffered raw with one reservation per warp.  A sample: the first round only.
+                        const int nj = (m.sparse_n + KS_X_THREADS - 1) / KS_X_THREADS;
+                        const int nj_use = sample ? min(nj, 1) : nj;
+                        for (; gi < nj_use; gi += 4) {  // four rounds at a time: one tcgen05.ld, the Y gathers of all four in flight
+                            unsigned u[8];
+                            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                                         : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
+                                         : "r"(tmem_q + (unsigned)(dsub * KS_SP_COLS + 2 * gi)) : "memory");
+                            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                            bool keep[4];
+                            float yt[4], yc[4], yd[4];
+#pragma unroll
+                            for (int r = 0; r < 4; r++) {  // (rounds behind the last one hold pairs of earlier panels)
+                                keep[r] = gi + r < nj_use && u[2 * r] != 0xffffffffu && u[2 * r + 1] != kSentinelBits;
+                                yt[r] = yc[r] = yd[r] = 0.f;
+                                if (keep[r] && flt) {
+                                    if (useT) yt[r] = __ldg(q.Yt + (int)u[2 * r]);
+                                    if (useC) yc[r] = __ldg(q.Yc + (int)u[2 * r]);
+                                    if (useD) yd[r] = __ldg(q.Yd + (int)u[2 * r]);
+                                }
+                            }
+                            unsigned bal[4];
+                            int tot = 0;
+#pragma unroll
+                            for (int r = 0; r < 4; r++) {
+                                if (keep[r] && flt) keep[r] = !slot_rejected<KIND>(q, fr, __uint_as_float(u[2 * r + 1]), lo_u, yt[r], yc[r], yd[r]);
+                                bal[r] = __ballot_sync(0xffffffffu, keep[r]);
+                                tot += __popc(bal[r]);
+                            }
+                            if (tot != 0) {
+                                int pos = 0;
+                                if (lane == 0) pos = atomicAdd(&s_cnt, tot);
+                                pos = __shfl_sync(0xffffffffu, pos, 0);
+                                if (pos + tot > KS_CAP) {  // does not fit: dead fillers, select, come back to these rounds
+                                    for (int i = pos + lane; i < min(pos + tot, KS_CAP); i += 32) cand[i] = 0xffffffffull;
+                                    overflow = true;
+                                    break;
+                                }
+#pragma unroll
+                                for (int r = 0; r < 4; r++) {
+                                    if (keep[r]) cand[pos + __popc(bal[r] & ((1u << lane) - 1u))] = make_raw(__uint_as_float(u[2 * r + 1]), (int)u[2 * r]);
+                                    pos += __popc(bal[r]);
+                                }
+                            }
+                        }
+                    } else {
+#endif
                     // coarse bound of THIS LANE's slots of the panel (it holds quads lane, lane + 128, ... of its quarter): a slot
                     // can only enter the result if  x >= lo * den  and  den >= Dmin + cX * x  with Dmin from the minima of Y over
                     // the lane's columns, i.e.  x * (1 - lo * cX) >= lo * Dmin.  A register per lane: the sweep below needs no
@@ -1108,6 +1265,9 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
                     }
                     while (!overflow && qn > 0)
                         if (!batch()) overflow = true;
+#if SPY_KS_SPARSE
+                    }
+#endif
                     if (overflow && lane == 0) s_overflow = 1;
                     ks_dsync();  // every drain warp is done or stopped at a full buffer
                     const bool again = *reinterpret_cast<volatile int *>(&s_overflow) != 0;
@@ -1148,7 +1308,9 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
                     n_eval = 0; tau = 0ull; lo = reject_bound(q, tau);
                     ks_dsync();
                 };
-                if (SPY_KS_SPEC && filter && tau == 0ull && n_eval == 0 && nG >= 2 * DPQ) {  // (uniform over the drain warps)
+                // (a sparse panel: worth a guess from 4 rounds of pairs on)
+                const bool spec_geom = (SPY_KS_SPARSE && m.sparse_n >= 0) ? m.sparse_n >= 4 * KS_X_THREADS : nG >= 2 * DPQ;
+                if (SPY_KS_SPEC && filter && tau == 0ull && n_eval == 0 && spec_geom) {  // (uniform over the drain warps)
 #if SPY_KS_HINT
                     // (a) the bound that the first panel of this CTA's previous row validated: consecutive rows of one matrix
                     //     look alike, and a wrong guess only costs the sweep that finds it out
@@ -1173,7 +1335,9 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
                     evaluate(cnt);
                     ks_dsync();
                     const int width = min(q.W, q.n_cols - base);
-                    const float f = (float)(KS_S_WARPS * 128) / (float)max(width, 1), kf = (float)q.k * f;
+                    const float f = (SPY_KS_SPARSE && m.sparse_n >= 0) ? (float)KS_X_THREADS / (float)max(m.sparse_n, 1)
+                                                                       : (float)(KS_S_WARPS * 128) / (float)max(width, 1);
+                    const float kf = (float)q.k * f;
 #ifdef SPY_SPEC_FORCE_RANK  // test builds: a bound that is almost never valid, to exercise the re-sweep
                     const int r_s = SPY_SPEC_FORCE_RANK;
 #else
