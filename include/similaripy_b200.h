@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SPY_ABI_VERSION 6
+#define SPY_ABI_VERSION 7
 
 typedef enum {
     SPY_OK = 0,
@@ -263,6 +263,25 @@ int spy_csr_filter_count_dev(int32_t n_rows, const int32_t *indptr, const int32_
 int spy_csr_filter_compact_dev(int32_t n_rows, const int32_t *indptr, const int32_t *indices, const float *data,
                                const uint8_t *col_mask, int drop_zeros, const int32_t *new_indptr,
                                int32_t *new_indices, float *new_data, void *stream);
+/* ---- matrices with more than 2^31-1 stored entries (64-bit indptr) -----------------------------
+ * The reference narrows indptr / indices to int32 (s_plus.pyx:241-244) and its kernel is <int,float>
+ * (s_plus.pyx:360), so such a matrix overflows there.  Here it is cut into int32-indexed BLOCKS that keep the
+ * shape of the whole matrix: block [lo, hi) of the stored entries keeps those entries and leaves every other
+ * row empty; its indices / values are the views indices + lo, data + lo of the 64-bit matrix and
+ *   block_indptr[r] = clamp(indptr[r], lo, hi) - lo           (r = 0..n_rows, so n = n_rows + 1)
+ * comes from spy_csr_wide_block_indptr_dev.  Pieces that are populated on disjoint row ranges and stored one
+ * after the other are stacked by adding their indptr arrays (spy_csr_indptr_add_dev: acc[r] += piece[r]).
+ * Target rows are computed block by block of matrix1's rows; the columns of matrix2 block by block, each
+ * giving the best k of its columns, merged by spy_slab_merge_dev. */
+int spy_csr_wide_block_indptr_dev(int64_t n, const int64_t *indptr, int64_t lo, int64_t hi, int32_t *out, void *stream);
+int spy_csr_indptr_add_dev(int64_t n, const int32_t *piece, int32_t *acc, void *stream);
+/* Best k of two slabs over DISJOINT column sets, both with their rows best-first (value descending, then
+ * column ascending -- the order every kernel of this library writes): the k largest values of the union
+ * (TopK, s_plus.h:45-59), rows padded with (0, 0.0) like the reference's slab (s_plus.pyx:351-353).
+ * out_* must not alias the inputs. */
+int spy_slab_merge_dev(int32_t n_targets, int32_t k, const int32_t *cols_a, const float *vals_a, const int32_t *counts_a,
+                       const int32_t *cols_b, const float *vals_b, const int32_t *counts_b, int32_t *out_cols,
+                       float *out_vals, int32_t *out_counts, void *stream);
 /* dtype conversion of values: binary => ones (s_plus_utils.pyx:281-308) */
 int spy_cast_values_dev(int64_t n, const void *src, int src_dtype, int binary, float *dst, void *stream);
 

@@ -33,6 +33,10 @@ KERNEL_TRACE = None
 
 MODE_NONE, MODE_ARRAY, MODE_MATRIX = _lib.SEL_NONE, _lib.SEL_ARRAY, _lib.SEL_MATRIX
 INT32_MAX = np.iinfo(np.int32).max
+# A stored matrix with more entries than this keeps a 64-bit indptr (WideCSR) and is computed in int32-indexed blocks of
+# at most this many entries (the reference narrows to int32, s_plus.pyx:241-244, and overflows).  Tests
+# lower it to drive small matrices through the block path.
+WIDE_NNZ_LIMIT = INT32_MAX
 
 
 def _torch():
@@ -162,6 +166,79 @@ class DeviceCSR:
         value = build()
         self.cache[key] = (partner, value)
         return value
+
+
+@dataclass
+class WideCSR(DeviceCSR):
+    """A CSR matrix with more than WIDE_NNZ_LIMIT stored entries: int64 indptr, int32 indices, float32 data.  The int32
+    kernels never see it whole: `wide_blocks` cuts it into DeviceCSR blocks that keep its shape (see there)."""
+
+    def host_indptr(self) -> np.ndarray:
+        return self.cached("indptr_host", lambda: self.indptr.cpu().numpy())
+
+
+def _greedy_cuts(prefix: np.ndarray, limit: int, what: str) -> list:
+    """Cut positions 0 = c[0] < c[1] < ... = n such that prefix[c[i+1]] - prefix[c[i]] <= limit (prefix: int64 exclusive
+    prefix sums with n + 1 entries)."""
+    n = prefix.shape[0] - 1
+    cuts = [0]
+    while cuts[-1] < n:
+        lo = cuts[-1]
+        hi = int(np.searchsorted(prefix, prefix[lo] + limit, side="right")) - 1
+        if hi <= lo:
+            raise ValueError(f"one {what} holds more than {limit} stored entries: it cannot be indexed with int32")
+        cuts.append(min(hi, n))
+    return cuts
+
+
+def wide_blocks(ctx: "Ctx", m: WideCSR, along_major: bool) -> list:
+    """[(lo, hi, DeviceCSR)]: m cut into int32-indexed blocks of at most WIDE_NNZ_LIMIT entries along its rows
+    (along_major) or its columns.  Every block has the SHAPE of m and holds the entries of rows (columns) [lo, hi); all
+    other rows (columns) are empty in it, so row and column ids, norm vectors, selectors and target lists keep their
+    meaning and the int32 kernels run on a block unchanged.  A row block is a zero-copy view: its indptr is
+    clamp(indptr, first, last) - first, its indices / values are slices.  A column block filters every row block by the
+    column range and stacks the pieces.  Explicit zeros are dropped like upload_stored does (s_plus.pyx:210-211)."""
+    torch, lib, limit = ctx.torch, ctx.lib, int(WIDE_NNZ_LIMIT)
+
+    def row_block(r0, r1, ip):
+        first, last = int(ip[r0]), int(ip[r1])
+        indptr = ctx.empty(m.n_rows + 1, torch.int32)
+        _lib.check(lib.spy_csr_wide_block_indptr_dev(m.n_rows + 1, _ptr(m.indptr), first, last, _ptr(indptr), ctx.sptr))
+        return DeviceCSR(m.n_rows, m.n_cols, indptr, m.indices[first:last], m.data[first:last], sorted_rows=m.sorted_rows)
+
+    def build():
+        ip = m.host_indptr()
+        rows = _greedy_cuts(ip, limit, "row")
+        if along_major:
+            return [(r0, r1, filter_csr(ctx, row_block(r0, r1, ip), drop_zeros=True)) for r0, r1 in zip(rows[:-1], rows[1:])]
+        counts = ctx.empty(max(m.n_cols, 1), torch.int32)[: m.n_cols]
+        _lib.check(lib.spy_csr_col_count_dev(m.nnz, _ptr(m.indices), m.n_cols, _ptr(counts), ctx.sptr))
+        prefix = np.zeros(m.n_cols + 1, dtype=np.int64)
+        np.cumsum(counts.cpu().numpy(), out=prefix[1:])
+        out = []
+        cols = _greedy_cuts(prefix, limit, "column")
+        for c0, c1 in zip(cols[:-1], cols[1:]):
+            mask = ctx.zeros(max(m.n_cols, 1), torch.uint8)
+            mask[c0:c1] = 1
+            indptr = ctx.zeros(m.n_rows + 1, torch.int32)
+            idx, val = [], []
+            for r0, r1 in zip(rows[:-1], rows[1:]):
+                piece = filter_csr(ctx, row_block(r0, r1, ip), col_mask=mask, drop_zeros=True)
+                _lib.check(lib.spy_csr_indptr_add_dev(m.n_rows + 1, _ptr(piece.indptr), _ptr(indptr), ctx.sptr))
+                idx.append(piece.indices)
+                val.append(piece.data)
+            out.append((c0, c1, DeviceCSR(m.n_rows, m.n_cols, indptr, torch.cat(idx), torch.cat(val), sorted_rows=m.sorted_rows)))
+        return out
+    return m.cached(("blocks", bool(along_major), limit), build)
+
+
+def operand_blocks(ctx: "Ctx", stored: DeviceCSR, transposed: bool, axis: int) -> list:
+    """[(lo, hi, DeviceMatrix)] covering logical axis `axis` (0: rows, 1: columns) of the operand (stored, transposed); a
+    matrix that fits int32 indexing is its own single block."""
+    n = (stored.n_cols, stored.n_rows)[axis] if transposed else (stored.n_rows, stored.n_cols)[axis]
+    if not isinstance(stored, WideCSR):
+        return [(0, n, DeviceMatrix(stored, transposed))]
+    return [(lo, hi, DeviceMatrix(b, transposed)) for lo, hi, b in wide_blocks(ctx, stored, along_major=(axis == 0) != transposed)]
 
 
 class DeviceMatrix:
@@ -302,8 +379,12 @@ def upload_stored(ctx: Ctx, matrix):
         matrix = matrix.tocsr()
         fmt = "csr"
     major, minor = (matrix.shape if fmt == "csr" else matrix.shape[::-1])
-    if max(matrix.shape) > INT32_MAX or matrix.nnz > INT32_MAX:
-        raise ValueError("matrix dimensions / nnz exceed int32, which the similarity kernel (like the reference) uses")
+    if max(matrix.shape) > INT32_MAX:
+        raise ValueError("matrix dimensions exceed int32, which the similarity kernel (like the reference) uses")
+    if matrix.nnz > WIDE_NNZ_LIMIT:  # 64-bit indptr; computed in int32-indexed blocks (wide_blocks)
+        return WideCSR(major, minor, ctx.h2d(np.asarray(matrix.indptr, dtype=np.int64)), _upload_index(ctx, matrix.indices),
+                       _upload_values(ctx, matrix.data, binary=False),
+                       sorted_rows=bool(getattr(matrix, "_has_sorted_indices", False))), fmt == "csc"
     m = DeviceCSR(major, minor, _upload_index(ctx, matrix.indptr), _upload_index(ctx, matrix.indices),
                   _upload_values(ctx, matrix.data, binary=False),
                   sorted_rows=bool(getattr(matrix, "_has_sorted_indices", False)))
@@ -325,11 +406,15 @@ def upload_pair(ctx: Ctx, matrix1, matrix2):
     """A = matrix1 and B = matrix2 as device CSR.  With matrix2=None (B = matrix1.T, s_plus.pyx:169-170)
     the data crosses PCIe once and is transposed once on the GPU, whichever of CSR / CSC matrix1 is."""
     s1, t1 = upload_stored(ctx, matrix1)
+    if isinstance(s1, WideCSR):
+        return s1, s1  # (refused by the caller: s_plus cuts such operands into blocks first)
     if matrix2 is None:  # A's row order is free; B is sorted later only if the plan has several panels
         other = cached_transpose(ctx, s1, sort=False)
         return (other, s1) if t1 else (s1, other)
     A = cached_transpose(ctx, s1, sort=False) if t1 else s1
     s2, t2 = upload_stored(ctx, matrix2)
+    if isinstance(s2, WideCSR):
+        return A, s2
     B = cached_transpose(ctx, s2) if t2 else s2
     return A, B
 
@@ -858,6 +943,8 @@ def prepare_job(matrix1, matrix2=None, weight_depop_matrix1="none", weight_depop
     ctx = Ctx(device)
     array_mode = selector_mode(filter_cols) == MODE_ARRAY or selector_mode(target_cols) == MODE_ARRAY
     A, B = upload_pair(ctx, matrix1, matrix2_given)
+    if isinstance(A, WideCSR) or isinstance(B, WideCSR):
+        raise ValueError("a matrix beyond int32 stored entries is computed block by block: call s_plus (or a similarity function)")
     raw_b = B.data if (binary and array_mode) else None
     if binary:
         A, B = binarize(ctx, A), binarize(ctx, B)
@@ -876,6 +963,91 @@ def prepare_job(matrix1, matrix2=None, weight_depop_matrix1="none", weight_depop
     return job
 
 
+def _is_wide(m) -> bool:
+    """True for an operand whose stored entries do not fit int32 indexing (scipy matrix or DeviceMatrix)."""
+    if isinstance(m, DeviceMatrix):
+        return isinstance(m.stored, WideCSR)
+    return sp.issparse(m) and m.nnz > WIDE_NNZ_LIMIT
+
+
+def _s_plus_wide(matrix1, matrix2, kw, target_rows, device, on_device):
+    """s_plus for operands with more than WIDE_NNZ_LIMIT stored entries.
+
+    Target rows are independent (s_plus.h:337-451), so matrix1 is taken one block of ROWS at a time; and the k best
+    columns of a row are the k best among the k best of every block of COLUMNS of matrix2 (TopK keeps the k largest
+    values, s_plus.h:45-59), so matrix2 is taken one block of columns at a time and the slabs are merged
+    (spy_slab_merge_dev).  Every block keeps the shape of its matrix (wide_blocks): ids, norm vectors, depop weights and
+    selectors are passed through unchanged, and each (row block, column block) call is an ordinary int32 job -- the
+    column sums of a column block and the row sums of a row block are complete, which is all computeSimilarity needs
+    (s_plus.h:129-156)."""
+    m2 = matrix2 if matrix2 is not None else matrix1.T
+    validate_inputs(matrix1, m2, kw["weight_depop_matrix1"], kw["weight_depop_matrix2"], kw["k"], target_rows,
+                    kw["filter_cols"], kw["target_cols"], kw["verbose"], kw["format_output"])
+    if _sharded.active() is not None:
+        raise NotImplementedError("sharded calls on matrices beyond int32 stored entries: shard the target rows yourself (target_rows)")
+    if dict(kw["tuning"] or {}).get("tie_mode", DEFAULT_TUNING.get("tie_mode", "deterministic")) == "reference":
+        raise NotImplementedError("tie_mode='reference' is limited to int32-indexed matrices, like the reference itself")
+    for name in ("filter_cols", "target_cols"):
+        if _is_wide(kw[name]):
+            raise NotImplementedError(f"{name} beyond int32 stored entries is not supported")
+    ctx = Ctx(device)
+    torch, lib = ctx.torch, ctx.lib
+    s1, t1 = upload_stored(ctx, matrix1)
+    s2, t2 = (s1, not t1) if matrix2 is None else upload_stored(ctx, matrix2)
+    a_blocks = operand_blocks(ctx, s1, t1, axis=0)
+    b_blocks = operand_blocks(ctx, s2, t2, axis=1)
+    n_rows, n_cols = int(matrix1.shape[0]), int(m2.shape[1])
+    k = int(min(kw["k"], n_cols))
+    if target_rows is None:
+        targets_np = np.arange(n_rows, dtype=np.int32)
+    else:
+        targets_np = np.ascontiguousarray(np.asarray(target_rows, dtype=np.int32))
+        if targets_np.size and (targets_np.min() < 0 or targets_np.max() >= n_rows):
+            raise ValueError(f"target_rows must lie in [0, {n_rows})")
+    n_t = int(targets_np.shape[0])
+    unique = target_rows is None or np.unique(targets_np).shape[0] == n_t
+    whole = len(a_blocks) == 1
+    slab = None if whole else (ctx.zeros(n_t * k, torch.int32), ctx.zeros(n_t * k, torch.float32), ctx.zeros(max(n_t, 1), torch.int32))
+    for r0, r1, a_blk in a_blocks:
+        if whole:
+            sel, rows = None, target_rows
+        else:
+            sel = np.nonzero((targets_np >= r0) & (targets_np < r1))[0]
+            rows = targets_np[sel]
+        n_loc = n_t if whole else int(sel.shape[0])
+        if n_loc == 0:
+            continue
+        acc = None
+        for _, _, b_blk in b_blocks:
+            job = prepare_job(a_blk, b_blk, target_rows=rows, device=ctx.device, **kw)
+            job.run()
+            cur = (job.out_cols, job.out_vals, job.out_counts)
+            if acc is None:
+                acc = cur
+            else:
+                out = (ctx.empty(n_loc * k, torch.int32), ctx.empty(n_loc * k, torch.float32), ctx.empty(n_loc, torch.int32))
+                _lib.check(lib.spy_slab_merge_dev(n_loc, k, _ptr(acc[0]), _ptr(acc[1]), _ptr(acc[2]), _ptr(cur[0]), _ptr(cur[1]),
+                                                  _ptr(cur[2]), _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), ctx.sptr))
+                acc = out
+            ctx.sync()  # the block job's tables are released before the next block builds its own
+            del job
+        if whole:
+            slab = acc
+        else:
+            at = ctx.h2d(sel.astype(np.int64))
+            slab[0].view(n_t, k).index_copy_(0, at, acc[0].view(n_loc, k))
+            slab[1].view(n_t, k).index_copy_(0, at, acc[1].view(n_loc, k))
+            slab[2][:n_t].index_copy_(0, at, acc[2][:n_loc])
+    if slab is None:  # no target rows at all
+        slab = (ctx.zeros(0, torch.int32), ctx.zeros(0, torch.float32), ctx.zeros(1, torch.int32))
+    fin = KnnJob(ctx=ctx, A=None, B=None, targets=ctx.h2d(targets_np), n_targets=n_t, k=k, n_rows=n_rows, n_cols=n_cols,
+                 params={}, unique_targets=unique)
+    fin.out_cols, fin.out_vals, fin.out_counts = slab
+    if on_device:
+        return fin.to_device_matrix()
+    return fin.to_host(fin.assemble_device(kw["format_output"]))
+
+
 @preserve_device
 def s_plus(matrix1, matrix2=None, weight_depop_matrix1="none", weight_depop_matrix2="none",
            p1=0.0, p2=0.0, a1=1.0, l1=0.0, l2=0.0, l3=0.0, t1=1.0, t2=1.0, c1=0.5, c2=0.5, k=100,
@@ -889,6 +1061,13 @@ def s_plus(matrix1, matrix2=None, weight_depop_matrix1="none", weight_depop_matr
     steer the reference's OpenMP team and CPU-cache blocking and have no meaning on the GPU
     (the shared-memory panel width is planned by the library).  ``verbose`` is validated and ignored.
     """
+    if _is_wide(matrix1) or _is_wide(matrix2):
+        return _s_plus_wide(matrix1, matrix2, dict(
+            weight_depop_matrix1=weight_depop_matrix1, weight_depop_matrix2=weight_depop_matrix2, p1=p1, p2=p2, a1=a1, l1=l1,
+            l2=l2, l3=l3, t1=t1, t2=t2, c1=c1, c2=c2, k=k, stabilized_shrink=stabilized_shrink, bayesian_shrink=bayesian_shrink,
+            additive_shrink=additive_shrink, threshold=threshold, binary=binary, filter_cols=filter_cols, target_cols=target_cols,
+            verbose=verbose, format_output=format_output, num_threads=num_threads, block_size=block_size, tuning=tuning),
+            target_rows, device, on_device)
     job = prepare_job(matrix1, matrix2, weight_depop_matrix1, weight_depop_matrix2, p1, p2, a1, l1, l2, l3, t1, t2,
                       c1, c2, k, stabilized_shrink, bayesian_shrink, additive_shrink, threshold, binary,
                       target_rows, filter_cols, target_cols, verbose, format_output, num_threads, block_size,
@@ -925,6 +1104,12 @@ def axis_sum(m: DeviceMatrix, axis: int):
     ctx = Ctx(m.device)
     torch, lib, s = ctx.torch, ctx.lib, m.stored
     along_stored_rows = (axis == 1) != m.transposed  # summing over the stored minor axis
+    if isinstance(s, WideCSR):  # block by block: every block has the shape of the matrix, the sums add up
+        total = None
+        for _, _, b in wide_blocks(ctx, s, along_major=True):
+            part = axis_sum(DeviceMatrix(b, m.transposed), axis)
+            total = part if total is None else total.add_(part)
+        return total
     if along_stored_rows:
         out = ctx.empty(s.n_rows, torch.float32)
         _lib.check(lib.spy_csr_row_sum_dev(s.n_rows, _ptr(s.indptr), _ptr(s.data), 0, _ptr(out), ctx.sptr))
@@ -950,6 +1135,8 @@ def to_host(m: DeviceMatrix):
     """DeviceMatrix -> scipy csr_array (or csc_array when the handle is a transposed view)."""
     s = m.stored
     arrs = [t.cpu().numpy() for t in (s.data, s.indices, s.indptr)]
+    if arrs[1].dtype != arrs[2].dtype:  # a 64-bit indptr: scipy wants one index dtype
+        arrs[1] = arrs[1].astype(arrs[2].dtype)
     if m.transposed:
         return sp.csc_array(tuple(arrs), shape=m.shape, dtype=np.float32)
     return sp.csr_array(tuple(arrs), shape=m.shape, dtype=np.float32)

@@ -77,6 +77,9 @@ SIGNATURES = {
     "spy_csr_sort_rows_dev": (C.c_int, [_i32, _vp, _vp, _vp, _vp]),
     "spy_csr_filter_count_dev": (C.c_int, [_i32, _vp, _vp, _vp, _vp, C.c_int, _vp, _vp]),
     "spy_csr_filter_compact_dev": (C.c_int, [_i32, _vp, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp]),
+    "spy_csr_wide_block_indptr_dev": (C.c_int, [_i64, _vp, _i64, _i64, _vp, _vp]),
+    "spy_csr_indptr_add_dev": (C.c_int, [_i64, _vp, _vp, _vp]),
+    "spy_slab_merge_dev": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "spy_cast_values_dev": (C.c_int, [_i64, _vp, C.c_int, C.c_int, _vp, _vp]),
     "spy_slab_row_nnz_dev": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "spy_slab_compact_dev": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp, _vp]),
@@ -88,7 +91,7 @@ SIGNATURES = {
                                    C.c_int, C.c_int, _f64, _vp, _vp]),
 }
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 ENGINE_AUTO, ENGINE_FLAT, ENGINE_STREAM = 0, 1, 2
 ERR_UNSUPPORTED = -4
 ENGINES = {"auto": ENGINE_AUTO, "flat": ENGINE_FLAT, "stream": ENGINE_STREAM}

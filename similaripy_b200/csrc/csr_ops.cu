@@ -427,6 +427,68 @@ __global__ void slab_fill_rows_kernel(int n_targets, int k, const int *__restric
     }
 }
 
+
+// ---- matrices beyond int32 stored entries (64-bit indptr): int32-indexed blocks ---------------
+// indptr of the block that keeps the stored entries [lo, hi) of a 64-bit CSR and leaves every other row empty:
+// out[r] = clamp(indptr[r], lo, hi) - lo.  The block has the shape of the whole matrix and shares its index / value
+// arrays (a view at offset lo), so the int32 kernels either side of the hot path run on it unchanged.
+__global__ void wide_block_indptr_kernel(long long n, const long long *__restrict__ indptr, long long lo, long long hi,
+                                         int *__restrict__ out) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) {
+        const long long v = indptr[r];
+        out[r] = (int)((v < lo ? lo : (v > hi ? hi : v)) - lo);
+    }
+}
+// indptr of pieces stacked on top of each other (each the full shape, populated on disjoint row ranges, entries
+// concatenated in piece order): the element-wise sum of the pieces' indptr arrays
+__global__ void indptr_add_kernel(long long n, const int *__restrict__ piece, int *__restrict__ acc) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) acc[r] += piece[r];
+}
+
+// ---- best k of two slabs (column blocks of matrix2 computed one after the other) ----------------
+// Both slabs hold their rows best-first in the key order of the hot kernels (value descending, then column ascending;
+// s_plus.h:45-59 keeps the k largest values), over DISJOINT column sets: an entry's place in the merged row is its own
+// position plus the number of entries of the other row that beat it (binary search).
+__device__ __forceinline__ unsigned long long merge_key(float v, int col) {
+    unsigned u = __float_as_uint(v);
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    return ((unsigned long long)u << 32) | (unsigned long long)(0xffffffffu - (unsigned)col);
+}
+__global__ void slab_merge_kernel(int n_targets, int k, const int *__restrict__ cols_a, const float *__restrict__ vals_a,
+                                  const int *__restrict__ counts_a, const int *__restrict__ cols_b,
+                                  const float *__restrict__ vals_b, const int *__restrict__ counts_b,
+                                  int *__restrict__ out_cols, float *__restrict__ out_vals, int *__restrict__ out_counts) {
+    const long long total = (long long)n_targets * 2 * k;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += stride) {
+        const int i = (int)(q / (2 * k)), e = (int)(q % (2 * k));
+        const bool from_b = e >= k;
+        const int j = from_b ? e - k : e;
+        const size_t o = (size_t)i * k;
+        const int na = counts_a[i], nb = counts_b[i];
+        const int n_out = min(k, na + nb);
+        if (j < (from_b ? nb : na)) {
+            const int *oc = from_b ? cols_a : cols_b;
+            const float *ov = from_b ? vals_a : vals_b;
+            const int on = from_b ? na : nb;
+            const int col = (from_b ? cols_b : cols_a)[o + j];
+            const float val = (from_b ? vals_b : vals_a)[o + j];
+            const unsigned long long key = merge_key(val, col);
+            int lo = 0, hi = on;  // entries of the other row with a larger key: the first `lo` of them
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (merge_key(ov[o + mid], oc[o + mid]) > key) lo = mid + 1; else hi = mid;
+            }
+            const int rank = j + lo;
+            if (rank < k) { out_cols[o + rank] = col; out_vals[o + rank] = val; }
+        }
+        if (e >= n_out && e < k) { out_cols[o + e] = 0; out_vals[o + e] = 0.f; }  // padding like the reference's slab (s_plus.pyx:351-353)
+        if (e == 0) out_counts[i] = n_out;
+    }
+}
+
 }  // namespace spy
 
 using namespace spy;
@@ -587,6 +649,36 @@ int spy_slab_fill_rows_dev(int32_t n_targets, int32_t k, const int32_t *targets,
     if (n_targets <= 0) return SPY_OK;
     slab_fill_rows_kernel<<<grid_for((long long)n_targets * k, kThreads * 4), kThreads, 0, as_stream(stream)>>>(n_targets, k, targets,
                                                                                                                counts, rows);
+    SPY_LAUNCH_OK();
+    return SPY_OK;
+}
+
+int spy_csr_wide_block_indptr_dev(int64_t n, const int64_t *indptr, int64_t lo, int64_t hi, int32_t *out, void *stream) {
+    if (n <= 0) return SPY_OK;
+    SPY_REQUIRE(indptr && out, "wide_block_indptr: NULL pointer");
+    SPY_REQUIRE(lo >= 0 && hi >= lo && hi - lo <= 2147483647LL, "wide_block_indptr: a block holds at most 2^31-1 entries");
+    wide_block_indptr_kernel<<<grid_for(n, kThreads), kThreads, 0, as_stream(stream)>>>(
+        n, reinterpret_cast<const long long *>(indptr), lo, hi, out);
+    SPY_LAUNCH_OK();
+    return SPY_OK;
+}
+
+int spy_csr_indptr_add_dev(int64_t n, const int32_t *piece, int32_t *acc, void *stream) {
+    if (n <= 0) return SPY_OK;
+    SPY_REQUIRE(piece && acc, "indptr_add: NULL pointer");
+    indptr_add_kernel<<<grid_for(n, kThreads), kThreads, 0, as_stream(stream)>>>(n, piece, acc);
+    SPY_LAUNCH_OK();
+    return SPY_OK;
+}
+
+int spy_slab_merge_dev(int32_t n_targets, int32_t k, const int32_t *cols_a, const float *vals_a, const int32_t *counts_a,
+                       const int32_t *cols_b, const float *vals_b, const int32_t *counts_b, int32_t *out_cols,
+                       float *out_vals, int32_t *out_counts, void *stream) {
+    if (n_targets <= 0 || k <= 0) return SPY_OK;
+    SPY_REQUIRE(cols_a && vals_a && counts_a && cols_b && vals_b && counts_b && out_cols && out_vals && out_counts,
+                "slab_merge: NULL pointer");
+    slab_merge_kernel<<<grid_for((long long)n_targets * 2 * k, kThreads), kThreads, 0, as_stream(stream)>>>(
+        n_targets, k, cols_a, vals_a, counts_a, cols_b, vals_b, counts_b, out_cols, out_vals, out_counts);
     SPY_LAUNCH_OK();
     return SPY_OK;
 }

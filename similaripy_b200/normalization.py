@@ -12,7 +12,7 @@ import numpy as np
 import scipy.sparse as sps
 
 from . import _lib
-from ._engine import Ctx, DeviceCSR, DeviceMatrix, _ptr, preserve_device, transpose_csr
+from ._engine import Ctx, DeviceCSR, DeviceMatrix, WideCSR, _ptr, preserve_device, transpose_csr
 
 _NORMALIZATIONS = ("l1", "l2", "max")
 _TF_MODES = ("binary", "raw", "sqrt", "freq", "log")
@@ -91,7 +91,15 @@ def _device_rows(X: DeviceMatrix, axis: int, inplace: bool):
     ctx = Ctx(X.device)
     want_transposed = (axis == 0)  # axis=0 normalises the rows of X.T
     s = X.stored
-    if X.transposed != want_transposed:  # stored orientation is the other one: transpose on the device (a copy)
+    if isinstance(s, WideCSR):  # beyond int32 stored entries (64-bit indptr): the stored orientation only
+        if X.transposed != want_transposed:
+            raise NotImplementedError("a DeviceMatrix beyond int32 stored entries is normalised along its stored rows only; "
+                                      "normalise the scipy matrix (64-bit indices are supported there) before to_device")
+        if not inplace:
+            s = WideCSR(s.n_rows, s.n_cols, s.indptr, s.indices, s.data.clone(), sorted_rows=s.sorted_rows)
+        else:
+            s.invalidate()
+    elif X.transposed != want_transposed:  # stored orientation is the other one: transpose on the device (a copy)
         s = transpose_csr(ctx, s)
     elif not inplace:
         s = DeviceCSR(s.n_rows, s.n_cols, s.indptr, s.indices, s.data.clone(), sorted_rows=s.sorted_rows, scatter_order=s.scatter_order)
@@ -102,6 +110,9 @@ def _device_rows(X: DeviceMatrix, axis: int, inplace: bool):
 
 def _device_weighting(X: DeviceMatrix, axis, inplace, bm25_args, tf_mode, idf_mode, logbase):
     _validate_modes(tf_mode, idf_mode)
+    if isinstance(X.stored, WideCSR):
+        raise NotImplementedError("tfidf / bm25 on a DeviceMatrix beyond int32 stored entries: weight the scipy matrix "
+                                  "(64-bit indices are supported there) before to_device")
     ctx, s, flag = _device_rows(X, axis, inplace)
     lib = ctx.lib
     scratch = ctx.empty(lib.spy_tfidf_scratch_bytes(s.n_rows, s.n_cols, _lib.F32), ctx.torch.uint8)
@@ -126,7 +137,7 @@ def normalize(X, norm: str = "l2", axis: int = 1, inplace: bool = False, *, devi
     if isinstance(X, DeviceMatrix):
         ctx, s, flag = _device_rows(X, axis, inplace)
         _lib.check(ctx.lib.spy_normalize_rows_dev(_NORMALIZATIONS.index(norm), s.n_rows, _ptr(s.data), _lib.F32,
-                                                  _ptr(s.indptr), _lib.I32, ctx.sptr))
+                                                  _ptr(s.indptr), _lib.I64 if isinstance(s, WideCSR) else _lib.I32, ctx.sptr))
         return DeviceMatrix(s, flag)
     X = _prepare_csr(X, axis, inplace)
     d = _DeviceRows(X, device, need_indices=False)
