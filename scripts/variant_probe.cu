@@ -108,6 +108,7 @@ int main(int argc, char **argv) {
     base.b_rows = R; base.n_cols = C; base.b_indptr = upload(b_indptr); base.b_indices = upload(b_indices); base.b_data = upload(b_data);
     base.Xcosine = upload(norm); base.Ycosine = base.Xcosine;
     base.a1 = 1.f; base.l2 = 1.f; base.t1 = 1.f; base.t2 = 1.f; base.k = k; base.b_nnz = nnz;
+    if (getenv("SPY_PROBE_DOT")) { base.l2 = 0.f; base.Xcosine = nullptr; base.Ycosine = nullptr; }  // plain dot product (configs[4]'s kind)
     const size_t slab = (size_t)n_t * k;
     int32_t *d_cols, *d_counts; float *d_vals;
     CK(cudaMalloc(&d_cols, slab * 4)); CK(cudaMalloc(&d_vals, slab * 4)); CK(cudaMalloc(&d_counts, (size_t)n_t * 4));

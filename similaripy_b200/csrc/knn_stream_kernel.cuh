@@ -86,6 +86,9 @@ struct KnnStreamDev {
 #ifndef SPY_KS_VECQ
 #define SPY_KS_VECQ 1    // the drain queues the passing quads of the four tiles of a group at once (0: tile by tile)
 #endif
+#ifndef SPY_KS_KEEPTAU
+#define SPY_KS_KEEPTAU 1  // a validated speculative bound stays the row's bound for the panels that follow
+#endif
 #ifndef SPY_KS_PREFETCH
 #define SPY_KS_PREFETCH 0  // bulk L2 prefetch of the next pass's segments: measured slower (43.1 vs 40.4 ms, profiles/r02)
 #endif
@@ -1322,6 +1325,11 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
                         if (done) {  // keep the bound where about 2 k candidates of a first panel beat it
                             if (above > 3 * q.k) hint += 0.08f * fabsf(hint);
                             else if (2 * above < 3 * q.k) hint -= 0.05f * fabsf(hint);
+#if SPY_KS_KEEPTAU
+                            // k buffered candidates beat the guess: it is a valid lower bound of the row's k-th best from here
+                            // on -- the next panels are swept with it instead of flooding the buffer into a forced selection
+                            tau = tau_h; lo = reject_bound(q, tau);
+#endif
                         }
                         else { forget(); hint_ok = false; KS_CNT(13, 1); }
                     }
@@ -1356,8 +1364,11 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
                         done = try_bound(tau_s) >= q.k;
                         KS_CNT(7, done ? 0 : 1);
                         if (!done) forget();
+#if SPY_KS_KEEPTAU
+                        if (done) { tau = tau_s; lo = reject_bound(q, tau); }
+#endif
 #if SPY_KS_HINT
-                        else { hint = unordered_bits((unsigned)(tau_s >> 32)); hint_ok = true; }
+                        if (done) { hint = unordered_bits((unsigned)(tau_s >> 32)); hint_ok = true; }
 #ifdef SPY_HINT_STRESS  // test builds: a carried bound that is (almost) never valid, to exercise its failure path
                         hint = 8.f * fabsf(hint) + 1.f;
 #endif
