@@ -546,7 +546,8 @@ def run_ours(args):
     if os.path.exists(traffic_file) and world == 1:  # dram bytes per launch from the committed ncu --set full capture
         try:
             tj = json.load(open(traffic_file))
-            if tj.get("kernel") == roofline["kernel"] and abs(tj.get("workload_nnz", 0) - nnz) <= 0.001 * nnz:
+            # ("kernel": "<kernel name> <version tag of the capture>")
+            if str(tj.get("kernel", "")).split(" ")[0] == roofline["kernel"] and abs(tj.get("workload_nnz", 0) - nnz) <= 0.001 * nnz:
                 roofline["traffic"] = tj.get("dram_bytes_per_launch")
                 roofline["traffic_source"] = tj.get("source")
         except Exception:

@@ -81,7 +81,15 @@ struct KnnStreamDev {
 #define SPY_KS_REGSORT 1  // the exact selection sorts in registers (shuffles; shared memory only for strides of 32 and more)
 #endif
 #ifndef SPY_KS_REDUCE
-#define SPY_KS_REDUCE 0   // 1: a filling buffer is cut by sampled pivots only (no sort) -- measured 1 % slower with 8 drain warps
+#define SPY_KS_REDUCE 0   // 1: a filling buffer is cut by sampled pivots only (no sort) -- measured 1 % slower with 8 drain warps, and
+                          // (together with SPY_KS_DEFER) 3-7 % slower with 16 (profiles/r02/probe_stream_y.txt)
+#endif
+#ifndef SPY_KS_DBUF
+#define SPY_KS_DBUF 1     // sparse hand-overs alternate between two TMEM regions: the expansion side runs up to two panels ahead
+#endif
+#ifndef SPY_KS_DEFER
+#define SPY_KS_DEFER 0    // 1: raw candidates are evaluated when a selection needs them, not at the end of every panel (two barriers
+                          // fewer per panel; measured: no gain -- the expansion side is the critical path, see REDUCE)
 #endif
 #ifndef SPY_KS_VECQ
 #define SPY_KS_VECQ 1    // the drain queues the passing quads of the four tiles of a group at once (0: tile by tile)
@@ -110,7 +118,7 @@ constexpr int KS_LIST_CAP = SPY_KS_SPARSE ? 6144 : 0;
 constexpr int KS_SP_J = (KS_LIST_CAP + KS_X_THREADS - 1) / KS_X_THREADS;  // pairs per thread
 constexpr int KS_SP_COLS = 2 * KS_SP_J;                                    // TMEM columns per (lane quarter, sub-group of warps)
 static_assert(!SPY_KS_SPARSE || SPY_KS_LOCAL, "the list holds slot offsets");
-static_assert(!SPY_KS_SPARSE || (KS_X_WARPS == KS_D_WARPS && KS_A_WARPS <= KS_CH / 32 && 4 * KS_SP_COLS <= 512 && KS_SP_J % 4 == 0),
+static_assert(!SPY_KS_SPARSE || (KS_X_WARPS == KS_D_WARPS && KS_A_WARPS <= KS_CH / 32 && 8 * KS_SP_COLS <= 512 && KS_SP_J % 4 == 0),
               "sparse hand-over: drain warp (quarter, sub) reads what expansion-side warp (quarter, sub) wrote");
 constexpr int KS_CAP = 1024;                   // candidate buffer (keys); k <= KS_CAP / 2
 constexpr int KS_S_WARPS = KS_D_WARPS < 8 ? KS_D_WARPS : 8;  // drain warps that take part in the sample of a first panel
@@ -431,7 +439,9 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
     unsigned short *list = reinterpret_cast<unsigned short *>(ptr);  // SPY_KS_SPARSE: slots touched for the first time in this panel
     (void)list;
 
-    __shared__ __align__(8) unsigned long long s_full, s_empty;
+    // hand-over n uses barrier pair n & 1 (and message slot n & 1): "full" is posted by the expansion side, "empty" collects
+    // the drain warps' releases.  Two pairs, because sparse hand-overs are double buffered in TMEM (SPY_KS_DBUF).
+    __shared__ __align__(8) unsigned long long s_full[2], s_empty[2];
     __shared__ __align__(8) u64 s_pivot;
     __shared__ KsPass s_pass[4];
     __shared__ KsQueue s_queue;
@@ -450,13 +460,13 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
     const float sentinel = __uint_as_float(kSentinelBits);
     const float4 sentinel4 = make_float4(sentinel, sentinel, sentinel, sentinel);
     const unsigned acc32 = (unsigned)__cvta_generic_to_shared(acc);
-    const unsigned full32 = (unsigned)__cvta_generic_to_shared(&s_full), empty32 = (unsigned)__cvta_generic_to_shared(&s_empty);
+    const unsigned full32 = (unsigned)__cvta_generic_to_shared(&s_full[0]), empty32 = (unsigned)__cvta_generic_to_shared(&s_empty[0]);  // pair 1: + 8
     const int nT = q.W >> 9;  // tiles of 512 columns (W is a multiple of 2048: whole groups of four tiles)
 
     for (int i = tid * 4; i < q.W; i += KS_NT * 4) *reinterpret_cast<float4 *>(acc + i) = sentinel4;
     if (tid == 0) {
-        ks_mbar_init(full32, 1);
-        ks_mbar_init(empty32, KS_D_WARPS);
+        ks_mbar_init(full32, 1); ks_mbar_init(full32 + 8u, 1);
+        ks_mbar_init(empty32, KS_D_WARPS); ks_mbar_init(empty32 + 8u, KS_D_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         s_cnt = 0; s_overflow = 0; s_live = 0; s_list_n[0] = 0; s_list_n[1] = 0;
 #if SPY_KS_LOCAL
@@ -688,10 +698,11 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
         // ---- snapshot bookkeeping (uniform over the warps of the side) ----
         unsigned seq = 0u;  // snapshots / messages posted so far
         bool panel_landed = false, m_landed = false;
+        bool prev_dense = false;  // the previous hand-over was a dense snapshot
         auto post = [&](int t, int i_out, int pn, int flags, int landed, int sparse_n) {  // one thread: message + "snapshot full"
             KsMsg *m = &s_msg[seq & 1u];
             m->t = t; m->i_out = i_out; m->pn = pn; m->flags = flags; m->landed = landed; m->sparse_n = sparse_n;
-            ks_mbar_arrive(full32);
+            ks_mbar_arrive(full32 + 8u * (seq & 1u));
         };
 #if SPY_KS_SPARSE
         bool listing = true;  // this warp still appends first touches to the list of the open panel (uniform over the warp)
@@ -713,8 +724,16 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
             const int n_list = -1;
             const bool sparse = false;
 #endif
-            // the drain must have released the previous snapshot (and read its message)
-            if (lane == 0) ks_mbar_wait(empty32, (seq & 1u) ^ 1u, p.err, 2);
+            // The drain must have released hand-over seq - 2 (its message slot, its barrier pair and -- for a sparse panel --
+            // its TMEM region are reused now), and hand-over seq - 1 as well unless both it and this one are sparse: a
+            // dense snapshot covers the whole of TMEM.
+            const bool dense_now = m_landed && !sparse;
+            if (lane == 0) {
+                ks_mbar_wait(empty32 + 8u * (seq & 1u), ((seq >> 1) & 1u) ^ 1u, p.err, 2);
+                if ((!SPY_KS_DBUF || dense_now || prev_dense) && seq >= 1u)
+                    ks_mbar_wait(empty32 + 8u * ((seq & 1u) ^ 1u), ((seq - 1u) >> 1) & 1u, p.err, 2);
+            }
+            prev_dense = dense_now;
             __syncwarp();
             KS_ACC(4, ts);
             ks_tc_fence_after();
@@ -750,7 +769,7 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
                         for (int r = 0; r < 4; r++)
                             if (sl[r] != 0xffffffffu) acc[sl[r]] = sentinel;
                         asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
-                                     ::"r"(tmem_q + (unsigned)(sub * KS_SP_COLS + 2 * j0)), "r"(col[0]), "r"(__float_as_uint(x[0])),
+                                     ::"r"(tmem_q + (unsigned)(sub * KS_SP_COLS + 2 * j0) + (SPY_KS_DBUF ? (seq & 1u) * (unsigned)(4 * KS_SP_COLS) : 0u)), "r"(col[0]), "r"(__float_as_uint(x[0])),
                                      "r"(col[1]), "r"(__float_as_uint(x[1])), "r"(col[2]), "r"(__float_as_uint(x[2])), "r"(col[3]),
                                      "r"(__float_as_uint(x[3])) : "memory");
                     }
@@ -949,7 +968,7 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
         }
         // no more rows: tell the drain
         if (tid == KS_DT) {
-            ks_mbar_wait(empty32, (seq & 1u) ^ 1u, p.err, 3);
+            ks_mbar_wait(empty32 + 8u * (seq & 1u), ((seq >> 1) & 1u) ^ 1u, p.err, 3);
             post(0, 0, 0, KS_FLAG_STOP, 0, -1);
         }
 #if SPY_KS_TIMING
@@ -980,6 +999,7 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
         u64 tau = 0ull;
         float lo = reject_bound(q, tau);
         int n_eval = 0;  // cand[0, n_eval) evaluated keys, cand[n_eval, s_cnt) raw candidates
+        int n_buf = 0;   // s_cnt as it stood when the previous panel of the row was done (uniform)
 #if SPY_KS_HINT
         float hint = 0.f;      // speculative bound (a similarity value) carried from row to row of this CTA; uniform
         bool hint_ok = false;
@@ -1018,7 +1038,7 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
 
         KS_T0(td);
         for (unsigned seq = 0u;; seq++) {
-            if (lane == 0) ks_mbar_wait(full32, seq & 1u, p.err, 1);
+            if (lane == 0) ks_mbar_wait(full32 + 8u * (seq & 1u), (seq >> 1) & 1u, p.err, 1);
             __syncwarp();
             KS_ACC(0, td);
             const KsMsg m = s_msg[seq & 1u];
@@ -1037,6 +1057,7 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
                 tau = 0ull;
                 lo = reject_bound(q, tau);
                 n_eval = 0;  // (s_cnt was reset when the previous row was written)
+                n_buf = 0;
             }
 #ifdef SPY_KS_NODRAIN  // timing experiment: the drain releases the snapshot unread (results are wrong)
             if (false) {
@@ -1063,7 +1084,7 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
                             unsigned u[8];
                             asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                                          : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
-                                         : "r"(tmem_q + (unsigned)(dsub * KS_SP_COLS + 2 * gi)) : "memory");
+                                         : "r"(tmem_q + (unsigned)(dsub * KS_SP_COLS + 2 * gi) + (SPY_KS_DBUF ? (seq & 1u) * (unsigned)(4 * KS_SP_COLS) : 0u)) : "memory");
                             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                             bool keep[4];
                             float yt[4], yc[4], yd[4];
@@ -1313,7 +1334,7 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
                 };
                 // (a sparse panel: worth a guess from 4 rounds of pairs on)
                 const bool spec_geom = (SPY_KS_SPARSE && m.sparse_n >= 0) ? m.sparse_n >= 4 * KS_X_THREADS : nG >= 2 * DPQ;
-                if (SPY_KS_SPEC && filter && tau == 0ull && n_eval == 0 && spec_geom) {  // (uniform over the drain warps)
+                if (SPY_KS_SPEC && filter && tau == 0ull && n_eval == 0 && n_buf == 0 && spec_geom) {  // (uniform over the drain warps)
 #if SPY_KS_HINT
                     // (a) the bound that the first panel of this CTA's previous row validated: consecutive rows of one matrix
                     //     look alike, and a wrong guess only costs the sweep that finds it out
@@ -1380,17 +1401,32 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
                 if (!done) sweep(0.f, false);
             }
             KS_ACC(1, td);
+#if SPY_KS_DEFER
+            // Every path above ends behind a barrier of the drain warps that follows the last append, and nobody appends
+            // again before the NEXT snapshot -- which the expansion side can only post after every drain warp's arrival
+            // below: the count read here is final and the same in all warps.
+            const int cnt = min(*reinterpret_cast<volatile int *>(&s_cnt), KS_CAP);
+#endif
             // the snapshot has been read: hand TMEM back (and with it the message slot)
             ks_tc_fence_before();
             __syncwarp();
-            if (lane == 0) ks_mbar_arrive(empty32);
+            if (lane == 0) ks_mbar_arrive(empty32 + 8u * (seq & 1u));
+#if SPY_KS_DEFER
+            // tighten the bound while the buffer is reasonably full; otherwise the raw candidates wait for the selection
+            // that needs them (a panel's end costs no barrier)
+            n_buf = cnt;
+            if (cnt > KS_CAP / 2 && !(m.flags & KS_FLAG_ROW_END)) { select_now(); n_buf = n_eval; KS_CNT(5, 1); }
+            else if (m.flags & KS_FLAG_ROW_END) { evaluate(cnt); ks_dsync(); }
+#else
             // evaluate what this panel added; tighten the bound while the buffer is reasonably full
             ks_dsync();
             {
                 const int cnt = min(*reinterpret_cast<volatile int *>(&s_cnt), KS_CAP);
-                if (cnt > KS_CAP / 2 && !(m.flags & KS_FLAG_ROW_END)) { select_now(); KS_CNT(5, 1); }
+                n_buf = cnt;
+                if (cnt > KS_CAP / 2 && !(m.flags & KS_FLAG_ROW_END)) { select_now(); n_buf = n_eval; KS_CNT(5, 1); }
                 else { evaluate(cnt); ks_dsync(); }
             }
+#endif
             KS_ACC(3, td);
             if (m.flags & KS_FLAG_ROW_END) {
                 // ---- final selection and slab write (s_plus.h:443-450) ----
