@@ -151,11 +151,23 @@ class ClockSampler:
         self.gpu_index = gpu_index
         self.proc = None
         self.lines = []
+        self.first = 0
+
+    def wait_ready(self, timeout_s=5.0):
+        """Block until nvidia-smi has delivered its first sample (it takes a few hundred ms to come up)."""
+        t0 = time.perf_counter()
+        while self.proc is not None and not self.lines and time.perf_counter() - t0 < timeout_s:
+            time.sleep(0.01)
+
+    def mark(self):
+        """The timed region starts now: only samples from here on count (nvidia-smi needs a few hundred ms to come up,
+        so it is started before the warm-up steps)."""
+        self.first = len(self.lines)
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -177,7 +189,10 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons, power = [], [], set(), []
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for ln in self.lines:
+        lines, note = self.lines[self.first:], None
+        if not lines and self.lines:  # a timed region shorter than the sampling period: the last samples of the warm-up steps
+            lines, note = self.lines[-3:], "timed region shorter than the sampling period: last samples of the warm-up steps (same load)"
+        for ln in lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -190,8 +205,11 @@ class ClockSampler:
                     reasons.add(name)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm), "power_w_max": float(max(power))}
+        out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+               "samples": len(sm), "power_w_max": float(max(power))}
+        if note:
+            out["note"] = note
+        return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -496,18 +514,20 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- device-resident timing ------------------------------------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        sampler.wait_ready()
     for _ in range(args.warmup):
         res = step_device()
     out_nnz = res.nnz
     del res
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     _engine.KERNEL_TRACE = []
     _lib.launch_count(reset=True)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark()
     ev0.record()
     for _ in range(args.steps):
         res = step_device()
