@@ -282,6 +282,9 @@ int spy_csr_indptr_add_dev(int64_t n, const int32_t *piece, int32_t *acc, void *
 int spy_slab_merge_dev(int32_t n_targets, int32_t k, const int32_t *cols_a, const float *vals_a, const int32_t *counts_a,
                        const int32_t *cols_b, const float *vals_b, const int32_t *counts_b, int32_t *out_cols,
                        float *out_vals, int32_t *out_counts, void *stream);
+/* int64 -> int32 index arrays on the device (the reference's host-side astype(int32), s_plus.pyx:241-244);
+ * the caller has checked that every value fits (matrix dimensions and stored entries within int32) */
+int spy_narrow_index_dev(int64_t n, const int64_t *src, int32_t *dst, void *stream);
 /* dtype conversion of values: binary => ones (s_plus_utils.pyx:281-308) */
 int spy_cast_values_dev(int64_t n, const void *src, int src_dtype, int binary, float *dst, void *stream);
 

@@ -297,8 +297,15 @@ def _upload_values(ctx: Ctx, data: np.ndarray, binary: bool):
 
 
 def _upload_index(ctx: Ctx, arr: np.ndarray):
+    """An index array as int32 on the device (s_plus.pyx:241-244).  A large int64 array is uploaded as it is and narrowed
+    by a kernel: the host-side astype(int32) of 2e8 entries costs several times the extra PCIe traffic."""
+    if arr.dtype == np.int64 and arr.nbytes >= STAGED_H2D_MIN_BYTES:
+        wide = ctx.h2d(arr)
+        out = ctx.empty(arr.shape[0], ctx.torch.int32)
+        _lib.check(ctx.lib.spy_narrow_index_dev(arr.shape[0], _ptr(wide), _ptr(out), ctx.sptr))
+        return out
     if arr.dtype != np.int32:
-        arr = arr.astype(np.int32)  # s_plus.pyx:241-244
+        arr = arr.astype(np.int32)
     return ctx.h2d(arr)
 
 

@@ -80,6 +80,7 @@ SIGNATURES = {
     "spy_csr_wide_block_indptr_dev": (C.c_int, [_i64, _vp, _i64, _i64, _vp, _vp]),
     "spy_csr_indptr_add_dev": (C.c_int, [_i64, _vp, _vp, _vp]),
     "spy_slab_merge_dev": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "spy_narrow_index_dev": (C.c_int, [_i64, _vp, _vp, _vp]),
     "spy_cast_values_dev": (C.c_int, [_i64, _vp, C.c_int, C.c_int, _vp, _vp]),
     "spy_slab_row_nnz_dev": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "spy_slab_compact_dev": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp, _vp]),

@@ -428,6 +428,13 @@ __global__ void slab_fill_rows_kernel(int n_targets, int k, const int *__restric
 }
 
 
+// int64 index arrays (scipy's choice for some large matrices) narrowed on the device: the reference narrows them on the host
+// (s_plus.pyx:241-244: astype(int32)), which costs more than uploading the wider array
+__global__ void narrow_index_kernel(long long n, const long long *__restrict__ src, int *__restrict__ dst) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = (int)src[i];
+}
+
 // ---- matrices beyond int32 stored entries (64-bit indptr): int32-indexed blocks ---------------
 // indptr of the block that keeps the stored entries [lo, hi) of a 64-bit CSR and leaves every other row empty:
 // out[r] = clamp(indptr[r], lo, hi) - lo.  The block has the shape of the whole matrix and shares its index / value
@@ -649,6 +656,14 @@ int spy_slab_fill_rows_dev(int32_t n_targets, int32_t k, const int32_t *targets,
     if (n_targets <= 0) return SPY_OK;
     slab_fill_rows_kernel<<<grid_for((long long)n_targets * k, kThreads * 4), kThreads, 0, as_stream(stream)>>>(n_targets, k, targets,
                                                                                                                counts, rows);
+    SPY_LAUNCH_OK();
+    return SPY_OK;
+}
+
+int spy_narrow_index_dev(int64_t n, const int64_t *src, int32_t *dst, void *stream) {
+    if (n <= 0) return SPY_OK;
+    SPY_REQUIRE(src && dst, "narrow_index: NULL pointer");
+    narrow_index_kernel<<<grid_for(n, kThreads * 4), kThreads, 0, as_stream(stream)>>>(n, reinterpret_cast<const long long *>(src), dst);
     SPY_LAUNCH_OK();
     return SPY_OK;
 }

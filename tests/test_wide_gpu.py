@@ -205,3 +205,21 @@ def test_real_size_beyond_int32_entries():
         crow = cos[[t]]
         np.testing.assert_allclose(np.sort(crow.data)[::-1], np.sort(cs)[::-1][:k], rtol=1e-5, err_msg=f"cosine row {t}")
         np.testing.assert_allclose(crow.data, cs[crow.indices], rtol=1e-5)
+
+
+def test_int64_index_arrays_are_narrowed_on_the_device(monkeypatch):
+    """scipy matrices with int64 indptr / indices below the int32 limits (s_plus.pyx:241-244 narrows them on the host):
+    large arrays are uploaded as they are and narrowed by spy_narrow_index_dev."""
+    m = random_csr(900, 700, 0.03, seed=31)
+    m64 = sp.csr_array((m.data, m.indices.astype(np.int64), m.indptr.astype(np.int64)), shape=m.shape)
+    want = sim.cosine(m, k=20, format_output="csr", verbose=False)
+    monkeypatch.setattr(_engine, "STAGED_H2D_MIN_BYTES", 1)  # every array takes the large-array path
+    before = _lib.launch_count()
+    got = sim.cosine(m64, k=20, format_output="csr", verbose=False)
+    assert _lib.launch_count() > before
+    assert_topk_parity(want, got, k=20, rtol=1e-6, what="int64-indexed input")
+    ref = oracle.similarity("cosine", m, k=20, format_output="csr", verbose=False)
+    assert_topk_parity(ref, got, k=20, rtol=1e-5, what="int64-indexed input vs oracle")
+    got_t = sim.cosine(m64.T, k=20, format_output="csr", verbose=False)  # CSC view with int64 arrays
+    ref_t = oracle.similarity("cosine", m.T.tocsr(), k=20, format_output="csr", verbose=False)
+    assert_topk_parity(ref_t, got_t, k=20, rtol=1e-5, what="int64-indexed CSC input vs oracle")
