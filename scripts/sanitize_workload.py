@@ -2,7 +2,7 @@
 panels, both CTA shapes), matrix filter / target selectors, normalizers.
     compute-sanitizer --tool memcheck  python scripts/sanitize_workload.py
     compute-sanitizer --tool racecheck python scripts/sanitize_workload.py
-Round 1 on B200: 0 errors, 0 hazards."""
+Round 1 on B200: 0 errors, 0 hazards.  Round 2 adds the stream kernel (both builds, dense + sparse hand-overs) and the block path."""
 import numpy as np, scipy.sparse as sp, sys
 sys.path.insert(0, '/root/repo')
 import similaripy_b200 as sim
@@ -22,3 +22,18 @@ tm = sp.random_array((300, 500), density=0.3, format="csr", dtype=np.float32, ra
 r = sim.dot_product(u2, s2, k=12, target_cols=tm, verbose=False, format_output="coo")
 w = sim.bm25(u2); w = sim.tfidf(u2); w = sim.normalize(u2, "l1")
 print("selectors + normalizers ok")
+# stream kernel, both builds: dense snapshots and double-buffered sparse hand-overs interleaved
+sys.path.insert(0, '/root/repo/tests')
+from test_stream_handover_gpu import _operands
+from similaripy_b200 import _engine
+a2, b2 = _operands(41)
+for dw in (8, 16):
+    for name in ("dot_product", "cosine"):
+        r = getattr(sim, name)(a2[:48], b2, k=40, verbose=False, format_output="csr", tuning=dict(engine="stream", drain_warps=dw, panel_width=10240))
+print("stream hand-overs ok", r.nnz)
+# matrices beyond int32 stored entries: the block path forced on a small matrix (row blocks x column blocks, slab merge)
+_engine.WIDE_NNZ_LIMIT = 3000
+m = sp.random_array((500, 400), density=0.05, format="csr", dtype=np.float32, random_state=rng)
+r = sim.cosine(m, k=20, verbose=False, format_output="csr")
+r = sim.cosine(m.T, k=20, verbose=False, format_output="csr")
+print("wide blocks ok", r.nnz)

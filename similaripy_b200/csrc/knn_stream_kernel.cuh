@@ -23,7 +23,8 @@
 //                         threshold (s_plus.h:206) and keep the best k (s_plus.h:45-59, 193-215), concurrently with
 //                         the expansion.  TMEM is read-only for the drain, so an overflowing candidate buffer just
 //                         selects and resumes.
-//   handshake: two mbarriers (snapshot full / snapshot free) and a two-entry message ring; named barriers inside the
+//   handshake: two pairs of mbarriers (snapshot full / snapshot free; hand-over n uses pair n & 1, so that sparse hand-overs
+//   can be double buffered in TMEM) and a two-entry message ring; named barriers inside the
 //   roles.  Every wait is bounded (trap + error flag) so that a protocol bug cannot hang the device.
 //
 // TMEM mapping of a panel: column c, quad q = c / 4, tile T = q / 128 (512 columns): lane = q % 128, TMEM column
@@ -1164,6 +1165,7 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
                             }
                             sm = survivor_mask<KIND>(q, fr, flt, lo_u, lc, la, x, yt, yc, yd);
                         }
+                        __syncwarp();  // the queue slots read above are written again by other lanes of the warp (tile())
                         const int c = __popc(sm);
                         int inc = c;
 #pragma unroll
