@@ -66,3 +66,25 @@ def test_engine_resolution_in_the_planner():
     assert rc < 0
     rc, _ = plan(threads=768)  # experiment builds only
     assert rc < 0 and b"threads must be" in lib.spy_last_error()
+
+
+def test_clock_sampler_counts_only_the_timed_region():
+    """bench.ClockSampler: nvidia-smi is started before the warm-up steps, mark() opens the timed region; a region shorter
+    than the sampling period falls back to the last samples of the warm-up steps and says so."""
+    line = lambda mhz, slow="Not Active": f"0, {mhz}, 1965, 700.0, 0x0, {slow}, Not Active, Not Active, Active"
+    s = bench.ClockSampler(0)
+    s.proc = type("P", (), {"terminate": lambda self: None, "wait": lambda self, timeout=None: 0, "kill": lambda self: None})()
+    s.lines = [line(1200), line(1500)]            # while nvidia-smi came up / warm-up
+    s.mark()
+    s.lines += [line(1965), line(1950), line(1965)]
+    out = s.stop()
+    assert out["sm_mhz"] == 1965.0 and out["samples"] == 3 and out["reasons"] == ["sw_power_cap"] and "note" not in out
+    s2 = bench.ClockSampler(0)
+    s2.proc = s.proc
+    s2.lines = [line(1800), line(1965, "Active")]
+    s2.mark()                                     # no sample inside the region
+    out2 = s2.stop()
+    assert out2["samples"] == 2 and "hw_slowdown" in out2["reasons"] and "shorter than the sampling period" in out2["note"]
+    s3 = bench.ClockSampler(0)
+    s3.proc = s.proc
+    assert s3.stop()["reasons"] == ["no samples"]
