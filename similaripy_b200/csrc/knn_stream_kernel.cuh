@@ -88,6 +88,9 @@ struct KnnStreamDev {
 #ifndef SPY_KS_DBUF
 #define SPY_KS_DBUF 1     // sparse hand-overs alternate between two TMEM regions: the expansion side runs up to two panels ahead
 #endif
+#ifndef SPY_KS_DEPTH
+#define SPY_KS_DEPTH 1    // batches of KS_U chunks per lane in flight (ring of KS_DEPTH * KS_U chunks per lane); 2 needs SPY_KS_SEARCH
+#endif
 #ifndef SPY_KS_DEFER
 #define SPY_KS_DEFER 0    // 1: raw candidates are evaluated when a selection needs them, not at the end of every panel (two barriers
                           // fewer per panel; measured: no gain -- the expansion side is the critical path, see REDUCE)
@@ -143,7 +146,7 @@ struct KsMsg {    // what the expansion side hands to the drain with every snaps
     int sparse_n;  // >= 0: the panel was handed over as that many (column, sum) pairs; -1: as a dense snapshot
 };
 
-__host__ __device__ constexpr size_t ks_ring_bytes() { return SPY_KS_RING ? (size_t)KS_A_WARPS * 32 * KS_U * 16 : 0; }
+__host__ __device__ constexpr size_t ks_ring_bytes() { return SPY_KS_RING ? (size_t)KS_A_WARPS * 32 * KS_U * 16 * SPY_KS_DEPTH : 0; }
 __host__ __device__ constexpr size_t ks_stage_bytes() { return (size_t)2 * (3 * KS_CH * 4 + 32 * 4); }
 __host__ __device__ constexpr size_t ks_queue_bytes() { return (size_t)KS_D_WARPS * KS_QCAP * (16 + 4); }
 __host__ __device__ constexpr size_t ks_pad_bytes() { return SPY_KS_LOCAL ? 16 : 0; }  // the slot filler pairs are added to
@@ -581,13 +584,23 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
         };
 
         // ---- expansion warp state ----
-        const unsigned slot32 = ring32 + (unsigned)((max(wa, 0) * 32 * KS_U + lane) * 16);  // chunk r of a batch: + r * 512
+        // chunk r of a batch: + r * 512; with SPY_KS_DEPTH == 2 the second batch in flight: + 512 * KS_U
+        const unsigned slot32 = ring32 + (unsigned)((max(wa, 0) * 32 * KS_U * SPY_KS_DEPTH + lane) * 16);
+        unsigned roff = 0u;  // ring half of the NEXT batch to issue (SPY_KS_DEPTH == 2)
         unsigned f = 0u, fb = 0u, F1 = 0u;  // next chunk to issue, end of the sub-batch, end of the warp's range (uniform)
         unsigned total = 0u;                // chunks of the pass
         float V = 0.f;
         const unsigned *cP = nullptr;  // staged pass
         float vp[KS_U];
         unsigned lp = 0u;
+#if SPY_KS_DEPTH == 2
+        static_assert(SPY_KS_RING && SPY_KS_SEARCH, "two batches in flight: the ring form with the bit-mask search");
+        float vq[KS_U];   // values / live chunks of the YOUNGER batch in flight (vp / lp: the older one)
+        unsigned lq = 0u;
+        int nfl = 0;      // batches in flight
+#pragma unroll
+        for (int r = 0; r < KS_U; r++) vq[r] = 0.f;
+#endif
 #if !SPY_KS_RING
         uint4 nx[KS_U];  // the batch in flight
 #pragma unroll
@@ -631,7 +644,7 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
                 vp[r] = __shfl_sync(0xffffffffu, V, j);
                 if (fr < fb) {
 #if SPY_KS_RING
-                    ks_cp_async16(slot32 + (unsigned)r * 512u, p.chunks + (dj + fr));
+                    ks_cp_async16(slot32 + roff + (unsigned)r * 512u, p.chunks + (dj + fr));
 #else
                     nx[r] = __ldg(p.chunks + (dj + fr));
 #endif
@@ -836,7 +849,25 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
             const unsigned v = prefix_at(blk * 32 + lane);
             j0 = blk * 32 + __popc(__ballot_sync(0xffffffffu, blk * 32 + lane <= n_cur && v <= F0)) - 1;
 #endif
+            roff = 0u;
             issue();
+#if SPY_KS_DEPTH == 2
+            // a second batch right behind the first: a short pass has all of its chunks in flight at once
+            nfl = 1;
+            if (f < F1) {
+                float va[KS_U];
+#pragma unroll
+                for (int r = 0; r < KS_U; r++) va[r] = vp[r];
+                const unsigned la = lp;
+                roff = 512u * KS_U;
+                issue();
+#pragma unroll
+                for (int r = 0; r < KS_U; r++) { vq[r] = vp[r]; vp[r] = va[r]; }
+                lq = lp; lp = la;
+                roff = 0u;
+                nfl = 2;
+            }
+#endif
             return true;
         };
 
@@ -886,16 +917,49 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
                 uint4 pr[KS_U];
                 float vc[KS_U];
 #if SPY_KS_RING
+#if SPY_KS_DEPTH == 2
+                if (nfl == 2) asm volatile("cp.async.wait_group 1;" ::: "memory"); else ks_cp_wait_all();
+#pragma unroll
+                for (int r = 0; r < KS_U; r++) { pr[r] = ks_lds128u(slot32 + roff + (unsigned)r * 512u); vc[r] = vp[r]; }
+#else
                 ks_cp_wait_all();
 #pragma unroll
                 for (int r = 0; r < KS_U; r++) { pr[r] = ks_lds128u(slot32 + (unsigned)r * 512u); vc[r] = vp[r]; }
+#endif
 #else
 #pragma unroll
                 for (int r = 0; r < KS_U; r++) { pr[r] = nx[r]; vc[r] = vp[r]; }
 #endif
                 const unsigned lc = lp;
+#if SPY_KS_DEPTH == 2
+                // the batch just read was the older one: the younger one (if any) takes its place, and the next batch of the
+                // warp's range goes into the ring half that has just been read
+                const bool two = nfl == 2;
+                nfl--;
+                if (nfl == 1) {
+#pragma unroll
+                    for (int r = 0; r < KS_U; r++) vp[r] = vq[r];
+                    lp = lq;
+                }
+                if (f < F1) {
+                    float va[KS_U];
+#pragma unroll
+                    for (int r = 0; r < KS_U; r++) va[r] = vp[r];
+                    const unsigned la = lp;
+                    issue();  // (into ring half roff; overwrites vp / lp)
+                    if (nfl == 1) {
+#pragma unroll
+                        for (int r = 0; r < KS_U; r++) { vq[r] = vp[r]; vp[r] = va[r]; }
+                        lq = lp; lp = la;
+                    }
+                    nfl++;
+                }
+                if (two) roff ^= 512u * KS_U;  // (the older batch of the two left in flight sits in the other half)
+                const bool more = nfl > 0;
+#else
                 const bool more = f < F1;
                 if (more) issue();
+#endif
 #if SPY_KS_SPARSE
                 bool first[2 * KS_U];
 #pragma unroll
