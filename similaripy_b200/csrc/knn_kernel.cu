@@ -4,26 +4,28 @@
 // Replaces s_plus::compute_similarities_parallel<int,float> (reference
 // similaripy/cython_code/s_plus.h:265-453) behind the C ABI in include/similaripy_b200.h.
 //
-// Design:
-//   * one persistent CTA per SM slot; CTAs pull target rows from an atomic queue
-//     (the reference's `omp for schedule(dynamic)`, s_plus.h:337);
-//   * the output columns are cut into panels of `panel_width` columns; a panel of fp32
-//     partial sums lives in shared memory (the reference's `sums` buffer, s_plus.h:91,
-//     at shared-memory instead of L2-cache scale, s_plus.h:305-311);
-//   * panel boundaries inside every sorted row of B are precomputed once (b_split) --
-//     the reference does a std::lower_bound per (target row, block, B row), s_plus.h:381-394;
-//   * the products of (target row, panel) are flattened into one index space by a block scan of
-//     the segment lengths, so every lane of every warp streams 8-byte (column, value) pairs
-//     whatever the segment lengths are; accumulation is a shared-memory float atomic
-//     (measured 538-605 Gproducts/s on B200, profiles/microbench/accum_bench_r01.txt);
-//   * "touched" is encoded in the accumulator itself: slots start at -0.0f, and
-//     (-0.0f) + x == x, so a slot whose bits are still 0x80000000 was never written
-//     (the reference keeps a touched-list, s_plus.h:112-117);
-//   * the drain applies filter / target selectors, computeSimilarity (s_plus.h:129-156) with
-//     the same operation order and no FMA contraction, the threshold test (s_plus.h:206), and
-//     feeds a running-threshold candidate buffer; a bitonic sort compacts it to the best k
-//     whenever it fills and once at the end of the row;
-//   * ties are resolved deterministically: larger value first, then smaller column id.
+// This file is the host side: the planner (engine choice, panel width, launch shape), the C-ABI entry points and the
+// launcher of the two kernel generations.  Design:
+//   * one persistent CTA per SM; CTAs pull target rows from an atomic queue (the reference's
+//     `omp for schedule(dynamic)`, s_plus.h:337);
+//   * the output columns are cut into panels of `panel_width` columns; a panel of fp32 partial sums lives in shared
+//     memory (the reference's `sums` buffer, s_plus.h:91, at shared-memory instead of L2-cache scale, s_plus.h:305-311);
+//   * panel boundaries inside every sorted row of B are precomputed once (b_split) -- the reference does a
+//     std::lower_bound per (target row, block, B row), s_plus.h:381-394;
+//   * accumulation is a shared-memory float add (LDS / FADD / ATOMS.CAST.SPIN, profiles/microbench/accum_bench_r01.txt);
+//     "touched" is encoded in the accumulator itself: slots start at -0.0f, and (-0.0f) + x == x, so a slot whose
+//     bits are still 0x80000000 was never written (the reference keeps a touched-list, s_plus.h:112-117);
+//   * STREAM engine (knn_stream_kernel.cuh, default): expansion and drain run on different warps of the CTA; the chunks
+//     of a pass are numbered through and cut into equal ranges per warp, streamed through a cp.async ring; a complete
+//     panel is handed to the drain through tensor memory (dense snapshot, or (column, sum) pairs for sparse panels);
+//   * FLAT engine (knn_kernel.cuh, round 1): a group of G lanes owns one entry of the target row at a time and streams the
+//     run of its B row inside the panel; expansion and drain alternate inside the CTA.  It keeps what the stream engine
+//     does not cover (matrix-mode target_cols, exact-only similarities, k > 512);
+//   * the drain applies filter / target selectors, computeSimilarity (s_plus.h:129-156) with the same operation order
+//     and no FMA contraction, the threshold test (s_plus.h:206), and feeds a running-threshold candidate buffer that is
+//     cut to the best k whenever it fills and once at the end of the row;
+//   * exact ties at the k-th value: larger value first, then smaller column id (identical sums only -- the float sums
+//     themselves depend on the order in which the adds land).
 #include "knn_stream_kernel.cuh"
 #include <algorithm>
 #include <cstdlib>
