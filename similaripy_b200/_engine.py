@@ -117,6 +117,21 @@ class Ctx:
     def sync(self):
         self.stream.synchronize()
 
+    # -- handles shared between calls (and streams) ---------------------------------------------------
+    def produced(self, csr):
+        """`csr` was written by kernels queued on this call's stream: remember where."""
+        ev = self.torch.cuda.Event()
+        ev.record(self.stream)
+        csr.ready = ev
+        return csr
+
+    def consume(self, csr):
+        """This call is about to read `csr` on its own stream: order it behind the stream that produced it."""
+        ev = getattr(csr, "ready", None)
+        if ev is not None:
+            self.stream.wait_event(ev)
+        return csr
+
     # -- small kernels ----------------------------------------------------------------------
     def scan_i32(self, counts):
         n = counts.numel()
@@ -147,6 +162,9 @@ class DeviceCSR:
     # every call): transposes, the row-sorted copy, squared norms / sums, the kernel's stream layouts and split
     # tables.  Anything that overwrites `data` in place must call invalidate().
     cache: dict = field(default_factory=dict, repr=False, compare=False)
+    # CUDA event recorded on the stream that produced (or last overwrote) the arrays; a call that consumes the handle on
+    # another stream waits for it first (Ctx.consume).  None: produced by a call that synchronised before it returned.
+    ready: object = field(default=None, repr=False, compare=False)
 
     @property
     def nnz(self) -> int:
@@ -380,7 +398,7 @@ def upload_stored(ctx: Ctx, matrix):
     if isinstance(matrix, DeviceMatrix):
         if matrix.device != ctx.device:
             raise ValueError(f"DeviceMatrix lives on {matrix.device}, the call runs on {ctx.device}")
-        return matrix.stored, matrix.transposed
+        return ctx.consume(matrix.stored), matrix.transposed
     fmt = getattr(matrix, "format", None)
     if fmt not in ("csr", "csc"):
         matrix = matrix.tocsr()
@@ -894,7 +912,7 @@ class KnnJob:
         _, indptr, indices, data = self.assemble_device("csr")
         if indices.dtype != self.ctx.torch.int32:
             raise ValueError("result exceeds int32 indexing; fetch it with on_device=False")
-        return DeviceMatrix(DeviceCSR(self.n_rows, self.n_cols, indptr, indices, data, sorted_rows=False), False)
+        return DeviceMatrix(self.ctx.produced(DeviceCSR(self.n_rows, self.n_cols, indptr, indices, data, sorted_rows=False)), False)
 
     def to_host(self, assembled):
         ctx = self.ctx
@@ -1109,7 +1127,7 @@ def to_device(matrix, device=None) -> DeviceMatrix:
 def axis_sum(m: DeviceMatrix, axis: int):
     """``matrix.sum(axis)`` of a DeviceMatrix as a float32 device tensor (similarity.py:479)."""
     ctx = Ctx(m.device)
-    torch, lib, s = ctx.torch, ctx.lib, m.stored
+    torch, lib, s = ctx.torch, ctx.lib, ctx.consume(m.stored)
     along_stored_rows = (axis == 1) != m.transposed  # summing over the stored minor axis
     if isinstance(s, WideCSR):  # block by block: every block has the shape of the matrix, the sums add up
         total = None
@@ -1133,7 +1151,9 @@ def pow_values_(m: DeviceMatrix, p: float) -> DeviceMatrix:
     """``m.data = m.data ** p`` in place on the device (similarity.py:411-415, 480-483)."""
     ctx = Ctx(m.device)
     d = m.stored.data
+    ctx.consume(m.stored)
     _lib.check(ctx.lib.spy_pow_shift_dev(d.numel(), _ptr(d), _lib.F32, 0.0, float(p), _ptr(d), ctx.sptr))
+    ctx.produced(m.stored)
     m.stored.invalidate()  # the values changed: cached transposes / norms / stream layouts are stale
     return m
 

@@ -90,7 +90,7 @@ def _device_rows(X: DeviceMatrix, axis: int, inplace: bool):
         raise ValueError(f"axis must be 0 or 1, got {axis}")
     ctx = Ctx(X.device)
     want_transposed = (axis == 0)  # axis=0 normalises the rows of X.T
-    s = X.stored
+    s = ctx.consume(X.stored)
     if isinstance(s, WideCSR):  # beyond int32 stored entries (64-bit indptr): the stored orientation only
         if X.transposed != want_transposed:
             raise NotImplementedError("a DeviceMatrix beyond int32 stored entries is normalised along its stored rows only; "
@@ -138,7 +138,7 @@ def normalize(X, norm: str = "l2", axis: int = 1, inplace: bool = False, *, devi
         ctx, s, flag = _device_rows(X, axis, inplace)
         _lib.check(ctx.lib.spy_normalize_rows_dev(_NORMALIZATIONS.index(norm), s.n_rows, _ptr(s.data), _lib.F32,
                                                   _ptr(s.indptr), _lib.I64 if isinstance(s, WideCSR) else _lib.I32, ctx.sptr))
-        return DeviceMatrix(s, flag)
+        return DeviceMatrix(ctx.produced(s), flag)
     X = _prepare_csr(X, axis, inplace)
     d = _DeviceRows(X, device, need_indices=False)
     _lib.check(d.ctx.lib.spy_normalize_rows_dev(_NORMALIZATIONS.index(norm), X.shape[0], _ptr(d.data), d.val_code,

@@ -197,6 +197,24 @@ def test_device_matrix_chain_matches_host_path():
         assert_topk_parity(ref, got, k=12, rtol=1e-5, what=f"device {name}")
 
 
+def test_handles_are_ordered_across_streams():
+    """A DeviceMatrix produced on one stream and consumed by a later call on another stream: the consumer waits for the
+    producer's event (Ctx.produced / Ctx.consume); the caller does not have to synchronise."""
+    import torch
+    urm = random_csr(3000, 1200, 0.02, seed=23)
+    host_model = oracle.similarity("cosine", urm.T.tocsr(), k=20, format_output="csr")
+    d = sim.to_device(urm)
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        model = sim.cosine(d.T, k=20, verbose=False, on_device=True)   # queued on `side`, nothing synchronises
+        sim.normalize(model, norm="l1", axis=1, inplace=True)          # in place, still on `side`
+    assert model.stored.ready is not None
+    rec = sim.dot_product(d, model.T, k=10, target_rows=[0, 7, 2999], verbose=False, format_output="csr")  # default stream
+    want_model = oracle.normalize(host_model, norm="l1", axis=1)
+    rec_ref = oracle.similarity("dot_product", urm, want_model.T.tocsr(), k=10, target_rows=[0, 7, 2999], format_output="csr")
+    assert_topk_parity(rec_ref, rec, k=10, rtol=1e-4, what="handle consumed on another stream")
+
+
 # ---- size-independent properties at a size the oracle cannot finish in seconds -------------------------
 def test_properties_at_scale():
     rng = np.random.default_rng(21)
