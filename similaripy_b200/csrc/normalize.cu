@@ -166,7 +166,8 @@ __global__ void __launch_bounds__(1024) sequential_mean_kernel(long long n, cons
             const T *b = buf[cur];
             int i = 0;
             for (; i + 8 <= m; i += 8) {  // loads first, then the dependent adds in row order (a version that loads the next
-                                          // eight values while the current eight are added was measured slower: 6.0 vs 5.1 ms)
+                                          // eight values while the current eight are added, and one that feeds the chain by
+                                          // warp shuffles, were measured slower: 6.0 and 6.5 vs 5.1 ms per bm25 call)
                 const T v0 = b[i], v1 = b[i + 1], v2 = b[i + 2], v3 = b[i + 3], v4 = b[i + 4], v5 = b[i + 5], v6 = b[i + 6], v7 = b[i + 7];
                 acc += v0; acc += v1; acc += v2; acc += v3; acc += v4; acc += v5; acc += v6; acc += v7;
             }
