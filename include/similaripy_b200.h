@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SPY_ABI_VERSION 7
+#define SPY_ABI_VERSION 8
 
 typedef enum {
     SPY_OK = 0,
@@ -141,6 +141,9 @@ typedef struct spy_knn_args {
                                  * spy_knn_build_aexp_dev                                                     */
     int64_t a_nnz;              /* stored entries of A (0 = unknown): with b_nnz the planner estimates the scalar
                                  * products per (target row, panel) and keeps short rows on the flat engine       */
+    int32_t unit_values;        /* non-zero: every stored value of A and B is 1.0 (binary=True, s_plus_utils.pyx:301-304).
+                                 * The stream engine then counts the products with native integer adds; results are
+                                 * bit-identical to the float path (sums of ones are exact).  0 is always correct.    */
 } spy_knn_args;
 
 #define SPY_ENGINE_AUTO 0

@@ -540,6 +540,7 @@ class KnnJob:
     exchange: object = None   # sharded.SlabExchange when the full result is gathered on every rank
     targets_np: object = None  # the FULL target list on the host (sharded runs)
     targets_key: object = None  # ("all", n) / ("range", lo, hi, n) when the target list is (a range of) all rows, else None
+    unit_values: bool = False   # binary=True: every stored value of A and B is 1.0 (the stream engine counts with integer adds)
 
     # ---- norm vectors (s_plus.pyx:259-269) ------------------------------------------------
     def build_vectors(self, weight_depop_matrix1, weight_depop_matrix2, p1, p2, c1, c2, additive_shrink):
@@ -711,6 +712,7 @@ class KnnJob:
         a.group = int(self.tuning.get("group", 0))
         a.b_nnz = B.nnz
         a.a_nnz = A.nnz
+        a.unit_values = 1 if (self.unit_values and self.tuning.get("unit_values", True)) else 0  # (tuning: A/B measurements)
         if self.tuning.get("tie_mode", "deterministic") == "reference":
             self._alloc_outputs(a)
             self.args = a
@@ -978,7 +980,8 @@ def prepare_job(matrix1, matrix2=None, weight_depop_matrix1="none", weight_depop
                   stabilized_shrink=f32(stabilized_shrink), bayesian_shrink=f32(bayesian_shrink), threshold=f32(threshold))
     job = KnnJob(ctx=ctx, A=A, B=B, targets=ctx.h2d(targets_np), n_targets=int(targets_np.shape[0]), k=k,
                  n_rows=n_rows, n_cols=n_cols, params=params, unique_targets=unique, tuning={**DEFAULT_TUNING, **dict(tuning or {})},
-                 targets_key=("all", n_rows) if target_rows is None else None)
+                 targets_key=("all", n_rows) if target_rows is None else None,
+                 unit_values=bool(binary) and raw_b is None)  # (list-mode selectors restore B's raw values: the a11 quirk)
     job.build_vectors(weight_depop_matrix1, weight_depop_matrix2, f32(p1), f32(p2), f32(c1), f32(c2), f32(additive_shrink))
     job.build_selectors(filter_cols, target_cols, raw_b)
     spec = _sharded.active()

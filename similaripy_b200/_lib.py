@@ -39,6 +39,7 @@ class KnnArgs(C.Structure):
         ("threads", _i32), ("b_pairs", _vp), ("row_order", _vp),
         ("b_nnz", _i64), ("group", _i32),
         ("engine", _i32), ("b_chunk_indptr", _vp), ("b_chunks", _vp), ("toff", _vp), ("n_entries", _i64), ("aexp", _vp), ("a_nnz", _i64),
+        ("unit_values", _i32),
     ]
 
 
@@ -92,7 +93,7 @@ SIGNATURES = {
                                    C.c_int, C.c_int, _f64, _vp, _vp]),
 }
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 ENGINE_AUTO, ENGINE_FLAT, ENGINE_STREAM = 0, 1, 2
 ERR_UNSUPPORTED = -4
 ENGINES = {"auto": ENGINE_AUTO, "flat": ENGINE_FLAT, "stream": ENGINE_STREAM}

@@ -122,6 +122,7 @@ constexpr int KS_LIST_CAP = SPY_KS_SPARSE ? 6144 : 0;
 constexpr int KS_SP_J = (KS_LIST_CAP + KS_X_THREADS - 1) / KS_X_THREADS;  // pairs per thread
 constexpr int KS_SP_COLS = 2 * KS_SP_J;                                    // TMEM columns per (lane quarter, sub-group of warps)
 static_assert(!SPY_KS_SPARSE || SPY_KS_LOCAL, "the list holds slot offsets");
+static_assert(SPY_KS_LOCAL, "the counting form of the panel (UNIT) is written for slot offsets in the chunks");
 static_assert(!SPY_KS_SPARSE || (KS_X_WARPS == KS_D_WARPS && KS_A_WARPS <= KS_CH / 32 && 8 * KS_SP_COLS <= 512 && KS_SP_J % 4 == 0),
               "sparse hand-over: drain warp (quarter, sub) reads what expansion-side warp (quarter, sub) wrote");
 constexpr int KS_CAP = 1024;                   // candidate buffer (keys); k <= KS_CAP / 2
@@ -421,7 +422,11 @@ static __device__ int ks_select(u64 *cand, int n, int k, u64 &tau, int *s_live, 
 #endif
 
 // The kernel.  KIND selects the drain's pre-filter like in knn_flat_kernel (KIND_RAW / _T / _C / _D / _GEN).
-template <int KIND>
+// UNIT: every stored value of A and B is 1.0 (binary=True, s_plus_utils.pyx:301-304): a product is exactly 1, so the panel
+// COUNTS with the native integer shared-memory add (ATOMS.ADD instead of the LDS / FADD / ATOMS.CAST.SPIN loop of a float
+// add); zero is the "untouched" mark, and the hand-over converts the counts to the floats the drain expects (exact below
+// 2^24, i.e. always: a count is bounded by the length of a row).
+template <int KIND, bool UNIT = false>
 __global__ void __launch_bounds__(KS_NT, 1)
 knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -463,18 +468,28 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
 #endif
     const float sentinel = __uint_as_float(kSentinelBits);
     const float4 sentinel4 = make_float4(sentinel, sentinel, sentinel, sentinel);
+    const float blank = UNIT ? 0.f : sentinel;  // an untouched slot of the shared-memory panel
+    const float4 blank4 = make_float4(blank, blank, blank, blank);
+    // count -> the float the drain expects (UNIT)
+    auto as_sum = [&](float raw) __attribute__((always_inline)) -> float {
+        const unsigned u = __float_as_uint(raw);
+        return u != 0u ? (float)u : sentinel;
+    };
+    (void)as_sum;
     const unsigned acc32 = (unsigned)__cvta_generic_to_shared(acc);
     const unsigned full32 = (unsigned)__cvta_generic_to_shared(&s_full[0]), empty32 = (unsigned)__cvta_generic_to_shared(&s_empty[0]);  // pair 1: + 8
     const int nT = q.W >> 9;  // tiles of 512 columns (W is a multiple of 2048: whole groups of four tiles)
 
-    for (int i = tid * 4; i < q.W; i += KS_NT * 4) *reinterpret_cast<float4 *>(acc + i) = sentinel4;
+    for (int i = tid * 4; i < q.W; i += KS_NT * 4) *reinterpret_cast<float4 *>(acc + i) = blank4;
     if (tid == 0) {
         ks_mbar_init(full32, 1); ks_mbar_init(full32 + 8u, 1);
         ks_mbar_init(empty32, KS_D_WARPS); ks_mbar_init(empty32 + 8u, KS_D_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         s_cnt = 0; s_overflow = 0; s_live = 0; s_list_n[0] = 0; s_list_n[1] = 0;
 #if SPY_KS_LOCAL
-        acc[q.W] = 0.f;  // the spare slot filler pairs add 0 to: never "untouched"
+        // the spare slot filler pairs add to: never "untouched" (the counting form adds 1 per filler: it starts at 1, so that
+        // the first filler is not taken for a first touch and listed)
+        acc[q.W] = UNIT ? __uint_as_float(1u) : 0.f;
 #endif
     }
     if (warp == 0) {
@@ -722,6 +737,11 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
         bool listing = true;  // this warp still appends first touches to the list of the open panel (uniform over the warp)
         // a product into the open panel; true: it was the first one to reach its slot (the add returned the "untouched" mark)
         auto add_first = [&](unsigned slot_off, float prod) __attribute__((always_inline)) -> bool {
+            if (UNIT) {
+                unsigned oldc;
+                asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(oldc) : "r"(accl + slot_off) : "memory");
+                return oldc == 0u;
+            }
             float old;
             asm volatile("atom.shared.add.f32 %0, [%1], %2;" : "=f"(old) : "r"(accl + slot_off), "f"(prod) : "memory");
             return __float_as_uint(old) == kSentinelBits;
@@ -758,7 +778,7 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
                     const int fs = __ldg(q.f_indptr + m_t), fe = __ldg(q.f_indptr + m_t + 1);
                     for (int x = fs + (tid - KS_DT); x < fe; x += KS_X_THREADS) {
                         const int c = __ldg(q.f_indices + x) - base;
-                        if (c >= 0 && c < width) acc[c] = sentinel;
+                        if (c >= 0 && c < width) acc[c] = blank;
                     }
                     ks_bar_sync(3, KS_X_THREADS);
                 }
@@ -777,11 +797,11 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
 #pragma unroll
                         for (int r = 0; r < 4; r++) {
                             col[r] = 0xffffffffu; x[r] = sentinel;
-                            if (sl[r] != 0xffffffffu) { x[r] = acc[sl[r]]; col[r] = (unsigned)base + sl[r]; }
+                            if (sl[r] != 0xffffffffu) { x[r] = UNIT ? as_sum(acc[sl[r]]) : acc[sl[r]]; col[r] = (unsigned)base + sl[r]; }
                         }
 #pragma unroll
                         for (int r = 0; r < 4; r++)
-                            if (sl[r] != 0xffffffffu) acc[sl[r]] = sentinel;
+                            if (sl[r] != 0xffffffffu) acc[sl[r]] = blank;
                         asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
                                      ::"r"(tmem_q + (unsigned)(sub * KS_SP_COLS + 2 * j0) + (SPY_KS_DBUF ? (seq & 1u) * (unsigned)(4 * KS_SP_COLS) : 0u)), "r"(col[0]), "r"(__float_as_uint(x[0])),
                                      "r"(col[1]), "r"(__float_as_uint(x[1])), "r"(col[2]), "r"(__float_as_uint(x[2])), "r"(col[3]),
@@ -791,8 +811,9 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
 #endif
                 for (int T = sub; T < nT; T += KS_X_WARPS / 4) {
                     const unsigned a = acc32 + (unsigned)(512 * T + 128 * (warp & 3) + 4 * lane) * 4u;
-                    const float4 x = lds128(a);
-                    sts128(a, sentinel4);
+                    float4 x = lds128(a);
+                    sts128(a, blank4);
+                    if (UNIT) x = make_float4(as_sum(x.x), as_sum(x.y), as_sum(x.z), as_sum(x.w));
                     ks_tmem_st4(tmem_q + (unsigned)(4 * T), x);
                 }
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -977,8 +998,13 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
                         first[2 * r] = add_first(pr[r].x, __fmul_rn(__uint_as_float(pr[r].y), vc[r]));
                         first[2 * r + 1] = add_first(pr[r].z, __fmul_rn(__uint_as_float(pr[r].w), vc[r]));
 #else
-                        smem_add_f32(accl + pr[r].x, __fmul_rn(__uint_as_float(pr[r].y), vc[r]));
-                        smem_add_f32(accl + pr[r].z, __fmul_rn(__uint_as_float(pr[r].w), vc[r]));
+                        if (UNIT) {
+                            asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(accl + pr[r].x) : "memory");
+                            asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(accl + pr[r].z) : "memory");
+                        } else {
+                            smem_add_f32(accl + pr[r].x, __fmul_rn(__uint_as_float(pr[r].y), vc[r]));
+                            smem_add_f32(accl + pr[r].z, __fmul_rn(__uint_as_float(pr[r].w), vc[r]));
+                        }
 #endif
 #endif
 #else

@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} is declared in the header but not exported"
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature in _lib.py"
     assert set(_lib.SIGNATURES) == set(declared)
-    assert lib.spy_abi_version() == _lib.ABI_VERSION == 7
+    assert lib.spy_abi_version() == _lib.ABI_VERSION == 8
 
 
 def test_struct_layout_matches_c(tmp_path):

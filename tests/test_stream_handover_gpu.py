@@ -31,13 +31,18 @@ def _operands(seed, n_u=2000, n_cols=25000, b_per_row=250):
 
 
 @pytest.mark.parametrize("drain_warps", [8, 16])
-@pytest.mark.parametrize("name,kw", [("dot_product", {}), ("cosine", {}), ("tversky", dict(alpha=0.7, beta=0.3))])
+@pytest.mark.parametrize("name,kw", [("dot_product", {}), ("cosine", {}), ("tversky", dict(alpha=0.7, beta=0.3)),
+                                     ("jaccard", dict(binary=True)), ("cosine", dict(binary=True)), ("dot_product", dict(binary=True))],
+                         ids=["dot", "cosine", "tversky", "jaccard_binary", "cosine_binary", "dot_binary"])
 def test_dense_and_sparse_handovers_interleaved(drain_warps, name, kw):
     a, b = _operands(41)
     tuning = dict(engine="stream", drain_warps=drain_warps, panel_width=10240)  # 3 panels: 10240 + 10240 + 4520 columns
     ref = oracle.similarity(name, a, b, k=40, format_output="csr", verbose=False, **kw)
     got = getattr(sim, name)(a, b, k=40, format_output="csr", verbose=False, tuning=tuning, **kw)
     assert_topk_parity(ref, got, k=40, rtol=1e-5, what=f"{name} D={drain_warps}")
+    if kw.get("binary"):  # the counting form of the panel (integer adds) against the float adds: bit-identical values
+        flt = getattr(sim, name)(a, b, k=40, format_output="csr", verbose=False, tuning=dict(tuning, unit_values=False), **kw)
+        assert np.array_equal(np.sort(flt.data), np.sort(got.data)) and flt.nnz == got.nnz
     # every long row must have produced more candidates than the sparse hand-over can list (else this test tests nothing)
     full = oracle.similarity("dot_product", a[[0]], b, k=25000, format_output="csr", verbose=False)
     assert full.nnz > 3 * 6144
