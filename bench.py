@@ -584,7 +584,7 @@ def run_ours(args):
 
         def timed_host(matrix, steps):
             call = lambda: sharded_call(lambda: sim.cosine(matrix.T, None, **common))
-            for _ in range(max(1, min(args.warmup, 2))):
+            for _ in range(max(1, args.warmup)):  # (all W warm-up steps: the first host-buffer calls also pin staging memory and, under torchrun, open the NCCL channels)
                 r = call()
             barrier()
             t0 = time.perf_counter()
