@@ -162,6 +162,27 @@ def test_cfg2_cosine_item_item_full_size():
     assert_topk_parity(ref, chk, k=k, rtol=1e-5, what="cfg2 oracle spot rows")
 
 
+def test_cfg2_jaccard_binary_full_size_counts_with_integer_adds():
+    """binary=True on the configs[1] URM (Jaccard item-item, k=100, 20 000 target rows): the stream engine counts the products
+    with native integer adds (csrc/knn_stream_kernel.cuh, UNIT); against the float64 restatement, the oracle's kernel, and
+    the float adds of the same engine (identical values: sums of ones are exact either way)."""
+    import torch
+    urm = _gen(1_000_000, 200_000, 1e-3, 2)
+    k = 100
+    rows = np.sort(np.random.default_rng(12).choice(200_000, size=20_000, replace=False)).astype(np.int32)
+    kw = dict(l1=1.0, t1=1.0, t2=1.0, binary=True)
+    job = _job(urm.T, None, k, rows, **kw)
+    assert job.out_counts.cpu().numpy().min() == k
+    _check_rows(job, [0, 9_999, 19_999], k, "cfg2 jaccard binary")
+    _oracle_rows(job, [5, 10_000, 19_998], k, "cfg2 jaccard binary")
+    if int(job.args.engine) == 2:
+        assert int(job.args.unit_values) == 1
+        flt = _job(urm.T, None, k, rows, tuning=dict(unit_values=False), **kw)
+        assert int(flt.args.unit_values) == 0
+        assert torch.equal(flt.out_counts, job.out_counts)
+        assert torch.equal(torch.sort(flt.out_vals.view(-1, k), dim=1).values, torch.sort(job.out_vals.view(-1, k), dim=1).values)
+
+
 def test_cfg3_s_plus_full_matrix_size():
     """configs[2]: s_plus(X, k=200, shrink=10), X 500k x 500k d=2e-3 (5e8 nnz, 10 column panels); 600 target rows."""
     x = _gen(500_000, 500_000, 2e-3, 3)
