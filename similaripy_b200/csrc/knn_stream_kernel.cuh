@@ -117,7 +117,17 @@ constexpr int KS_U = SPY_KS_U;                 // 16-byte chunks per lane per ba
 // Sparse panels (SPY_KS_SPARSE): the expansion lists the slots it touches for the first time; a panel with at most
 // KS_LIST_CAP touched slots is handed over as (column, sum) pairs -- KS_SP_J pairs per expansion-side thread, in the TMEM
 // lane of that thread -- instead of as a 160 KB snapshot that the drain has to sweep.
-constexpr int KS_CH = SPY_KS_SPARSE ? 512 : 1024;  // entries of a target row per pass (blocks of 32; the list takes the room)
+#ifndef SPY_KS_CH
+#define SPY_KS_CH (SPY_KS_SPARSE ? 512 : 1056)
+#endif
+// Entries of a target row per pass, in blocks of 32 (the sparse build: the list takes the room).  1056 rather than 1024: a row
+// of 1000 +- 32 entries -- the target rows of configs[1..3] -- then fits ONE pass per panel (3.8 % of them do not, against
+// 22 %); the few entries behind 1024 used to cost a second, nearly empty pass per panel (8.3k cycles each: +27 % on rows of
+// 1040 entries, profiles/r02/probe_ch.txt).  33 blocks is what the shared memory of the 5-panel plan has room for.
+constexpr int KS_CH = SPY_KS_CH;
+constexpr int KS_NB = KS_CH / 32;                  // staged blocks per pass: lane b keeps block b, lanes 0.. also block 32 + b
+constexpr int KS_NBT = KS_NB > 32 ? ((KS_NB + 1) / 2) * 2 : 32;  // block totals per staging buffer
+static_assert(KS_CH % 32 == 0 && KS_NB <= KS_NBT && (KS_NB <= 32 || SPY_KS_SEARCH), "pass size");
 constexpr int KS_LIST_CAP = SPY_KS_SPARSE ? 6144 : 0;
 constexpr int KS_SP_J = (KS_LIST_CAP + KS_X_THREADS - 1) / KS_X_THREADS;  // pairs per thread
 constexpr int KS_SP_COLS = 2 * KS_SP_J;                                    // TMEM columns per (lane quarter, sub-group of warps)
@@ -148,7 +158,7 @@ struct KsMsg {    // what the expansion side hands to the drain with every snaps
 };
 
 __host__ __device__ constexpr size_t ks_ring_bytes() { return SPY_KS_RING ? (size_t)KS_A_WARPS * 32 * KS_U * 16 * SPY_KS_DEPTH : 0; }
-__host__ __device__ constexpr size_t ks_stage_bytes() { return (size_t)2 * (3 * KS_CH * 4 + 32 * 4); }
+__host__ __device__ constexpr size_t ks_stage_bytes() { return (size_t)2 * (3 * KS_CH * 4 + KS_NBT * 4); }
 __host__ __device__ constexpr size_t ks_queue_bytes() { return (size_t)KS_D_WARPS * KS_QCAP * (16 + 4); }
 __host__ __device__ constexpr size_t ks_pad_bytes() { return SPY_KS_LOCAL ? 16 : 0; }  // the slot filler pairs are added to
 __host__ __device__ constexpr size_t ks_list_bytes() { return (size_t)KS_LIST_CAP * 2; }
@@ -421,6 +431,26 @@ static __device__ int ks_select(u64 *cand, int n, int k, u64 &tau, int *s_live, 
 #define KS_CNT(id, n) do { } while (0)
 #endif
 
+// Block search of the expansion for chunk f of a pass of more than 32 blocks, when f lies behind block 31: the totals of
+// blocks 32.. are read from the staging buffer (lane b: block 32 + b).  Returns the block, its word (chunks of the pass
+// up to and including it | staged segments << 26) and the word of the block before it.
+static __device__ __noinline__ void ks_block_behind_31(const unsigned *cP, unsigned f, unsigned bw, int lane, int &blk, unsigned &wb, unsigned &wp) {
+    const unsigned w2 = lane < KS_NB - 32 ? cP[3 * KS_CH + 32 + lane] : 0u;
+    unsigned inc2 = w2 & 0x3ffffffu;
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {  // (at most 8 blocks behind block 31)
+        const unsigned v = __shfl_up_sync(0xffffffffu, inc2, o);
+        if (lane >= o) inc2 += v;
+    }
+    const unsigned p1 = __shfl_sync(0xffffffffu, bw, 31);
+    const unsigned bw2 = (inc2 + (p1 & 0x3ffffffu)) | (w2 & 0xfc000000u);
+    const int b2 = __ffs(__ballot_sync(0xffffffffu, lane < KS_NB - 32 && (bw2 & 0x3ffffffu) > f)) - 1;
+    blk = 32 + b2;
+    wb = __shfl_sync(0xffffffffu, bw2, b2);
+    const unsigned p2 = __shfl_sync(0xffffffffu, bw2, max(b2 - 1, 0));
+    wp = b2 > 0 ? p2 : p1;
+}
+
 // The kernel.  KIND selects the drain's pre-filter like in knn_flat_kernel (KIND_RAW / _T / _C / _D / _GEN).
 // UNIT: every stored value of A and B is 1.0 (binary=True, s_plus_utils.pyx:301-304): a product is exactly 1, so the panel
 // COUNTS with the native integer shared-memory add (ATOMS.ADD instead of the LDS / FADD / ATOMS.CAST.SPIN loop of a float
@@ -437,9 +467,9 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
     ptr += ks_ring_bytes();
     // staged pass (double buffered): per entry the chunk count prefix INSIDE its block of 32 entries, the first chunk, the
     // value; per block the chunk total
-    // (buffer b at stage0 + b * KS_STAGE_WORDS: prefixes [KS_CH], first chunks [KS_CH], values [KS_CH], block totals [32];
+    // (buffer b at stage0 + b * KS_STAGE_WORDS: prefixes [KS_CH], first chunks [KS_CH], values [KS_CH], block totals [KS_NBT];
     // plain pointer arithmetic -- an array of pointers indexed by the buffer number would live in local memory)
-    constexpr int KS_STAGE_WORDS = 3 * KS_CH + 32;
+    constexpr int KS_STAGE_WORDS = 3 * KS_CH + KS_NBT;
     unsigned *const stage0 = reinterpret_cast<unsigned *>(ptr);
     ptr += 2 * KS_STAGE_WORDS * 4;
     float4 *qx_all = reinterpret_cast<float4 *>(ptr); ptr += (size_t)KS_D_WARPS * KS_QCAP * 16;
@@ -588,13 +618,14 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
             // queue warp's blocks empty, and scanning them one by one made it the last warp at the end-of-pass barrier
             const int nb = (d.n + 31) >> 5;
             if (lane >= max(nb, KS_A_WARPS)) stage0[buf * KS_STAGE_WORDS + 3 * KS_CH + lane] = 0u;
+            if (KS_NB > 32 && lane < KS_NB - 32 && 32 + lane >= max(nb, KS_A_WARPS)) stage0[buf * KS_STAGE_WORDS + 3 * KS_CH + 32 + lane] = 0u;
             for (int b0 = KS_A_WARPS; b0 < nb; b0 += 3) {
                 uint2 se[3];
                 float v[3];
 #pragma unroll
-                for (int r = 0; r < 3; r++) { se[r] = make_uint2(0u, 0u); v[r] = 0.f; if (b0 + r < 32) stage_fetch(d, b0 + r, se[r], v[r]); }
+                for (int r = 0; r < 3; r++) { se[r] = make_uint2(0u, 0u); v[r] = 0.f; if (b0 + r < KS_NB) stage_fetch(d, b0 + r, se[r], v[r]); }
 #pragma unroll
-                for (int r = 0; r < 3; r++) if (b0 + r < 32) stage_block(buf, b0 + r, se[r], v[r]);
+                for (int r = 0; r < 3; r++) if (b0 + r < KS_NB) stage_block(buf, b0 + r, se[r], v[r]);
             }
         };
 
@@ -630,12 +661,22 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
         // segment of chunk number f + x is  jprev + popc(starts at or before x),  jprev = the last segment that starts
         // before f.  Two warp reductions per batch instead of ten dependent shuffles of a binary search.
         unsigned bw = 0u;                   // lane b: chunks of the pass up to and including block b | staged segments of block b << 26
+        // (blocks 32.. of a pass of more than 32 blocks: their totals are re-read from the staging buffer by the few warps whose
+        // chunk range reaches them -- a register for them in every expansion warp costs spills in the loop below)
         unsigned Pe = 0xffffffffu, Dl = 0u; // lane l: first chunk number of segment l of the block; (its first chunk in `chunks`) - Pe
         int jprev = -1;
         auto issue = [&]() {  // one batch of KS_U chunks per lane into the ring
             if (f >= fb) {    // the block that holds chunk f (uniform); f < F1 <= total: it exists
-                const int blk = __ffs(__ballot_sync(0xffffffffu, (bw & 0x3ffffffu) > f)) - 1;
-                const unsigned wb = __shfl_sync(0xffffffffu, bw, blk), wp = __shfl_sync(0xffffffffu, bw, max(blk - 1, 0));
+                const unsigned in_first = __ballot_sync(0xffffffffu, (bw & 0x3ffffffu) > f);
+                int blk;
+                unsigned wb, wp;
+                if (KS_NB > 32 && in_first == 0u) {  // behind block 31 (rare: kept out of line, away from the registers of the loop)
+                    ks_block_behind_31(cP, f, bw, lane, blk, wb, wp);
+                } else {
+                    blk = __ffs(in_first) - 1;
+                    wb = __shfl_sync(0xffffffffu, bw, blk);
+                    wp = __shfl_sync(0xffffffffu, bw, max(blk - 1, 0));
+                }
                 const unsigned bend = wb & 0x3ffffffu, bo = blk > 0 ? (wp & 0x3ffffffu) : 0u;
                 const unsigned *sb = cP + blk * 32 + lane;
                 Pe = 0xffffffffu;
@@ -851,6 +892,16 @@ knn_stream_kernel(const __grid_constant__ KnnStreamDev p) {
             total = __shfl_sync(0xffffffffu, inc, 31);
 #if SPY_KS_SEARCH
             bw = inc | (w & 0xfc000000u);
+            if (KS_NB > 32) {  // blocks 32..: lane b keeps block 32 + b
+                const unsigned w2 = lane < KS_NB - 32 ? st[3 * KS_CH + 32 + lane] : 0u;
+                unsigned inc2 = w2 & 0x3ffffffu;
+#pragma unroll
+                for (int o = 1; o < 8; o <<= 1) {  // (at most 8 blocks behind block 31)
+                    const unsigned v = __shfl_up_sync(0xffffffffu, inc2, o);
+                    if (lane >= o) inc2 += v;
+                }
+                total += __shfl_sync(0xffffffffu, inc2, 7);
+            }
             if (is_queue) return false;
             cP = st;
             const unsigned F0 = (unsigned)(((unsigned long long)total * (unsigned)wa) / KS_A_WARPS);
