@@ -37,3 +37,14 @@ m = sp.random_array((500, 400), density=0.05, format="csr", dtype=np.float32, ra
 r = sim.cosine(m, k=20, verbose=False, format_output="csr")
 r = sim.cosine(m.T, k=20, verbose=False, format_output="csr")
 print("wide blocks ok", r.nnz)
+# passes of more than 32 staged blocks (target rows of 1025..1056 entries) and rows that need a second pass
+n_u = 3000
+b3 = sp.random_array((n_u, 6000), density=20 / 6000, format="csr", dtype=np.float32, random_state=rng)
+rows3, cols3 = [], []
+for r, n in enumerate((1030, 1056, 1057, 1100, 40, 2200)):
+    c = rng.choice(n_u, size=n, replace=False)
+    rows3 += [r] * n; cols3 += c.tolist()
+a3 = sp.csr_array((rng.random(len(rows3)).astype(np.float32) + 0.1, (np.asarray(rows3), np.asarray(cols3))), shape=(6, n_u))
+for dw in (8, 16):
+    r = sim.cosine(a3, b3, k=30, verbose=False, format_output="csr", tuning=dict(engine="stream", drain_warps=dw, panel_width=2048))
+print("long passes ok", r.nnz)
